@@ -1,0 +1,229 @@
+/*
+ * ncb.h -- C ABI of libncb: nanocompore's per-position two-condition comparison on B200.
+ *
+ * This is the drop-in boundary for ONE path of nanocompore v2.0.0:
+ *   Worker._prepare_data / _filter_low_cov_positions        nanocompore/run.py:511-515, 532-601
+ *   TranscriptComparator.compare_transcript                 nanocompore/comparisons.py:41-148
+ *     _add_shift_stats                                      comparisons.py:406-433
+ *     outlier filter + standardise                          comparisons.py:95-120
+ *     _nonparametric_test (KS / MW / TT via SciPy)          comparisons.py:218-252
+ *     _gmm_test_split (gmm_gpu.GMM, contingency, chi2, LOR) comparisons.py:338-392
+ *     _get_cluster_counts / _get_mod_cluster                comparisons.py:477-605
+ *   Postprocessor._multipletests_filter_nan (BH FDR)        nanocompore/postprocessing.py:255-285
+ *
+ * The reference has no FFI: it is pure Python calling torch / SciPy / gmm_gpu.  The
+ * entry points below are what a ctypes binding inside the reference's
+ * TranscriptComparator would call (INTEGRATION.md shows that stub).
+ *
+ * Conventions: plain pointers and sizes, no C++ / torch types; every function returns
+ * 0 on success or a negative ncb_status; nothing throws across the ABI;
+ * ncb_last_error() gives the message of the last failure on that handle.  The caller
+ * owns every buffer it passes in; the library owns its device scratch.  One handle per
+ * process per device; a handle is not thread-safe.
+ */
+#ifndef NCB_H
+#define NCB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCB_ABI_VERSION 1
+
+typedef struct ncb_handle ncb_handle;
+
+typedef enum {
+    NCB_OK = 0,
+    NCB_ERR_INVALID = -1,      /* bad argument                                          */
+    NCB_ERR_CUDA = -2,         /* CUDA runtime error (message in ncb_last_error)        */
+    NCB_ERR_NOMEM = -3,        /* device/pinned allocation failed (maps to torch.OutOfMemoryError) */
+    NCB_ERR_TOO_MANY_READS = -4 /* a position has more valid reads than NCB_MAX_READS   */
+} ncb_status;
+
+/* Most valid reads one position may hold (the reference caps at 5000 per condition,
+ * config.py:200 `downsample_high_coverage`, run.py:518-529). */
+#define NCB_MAX_READS 10240
+#define NCB_MAX_SAMPLES 64
+
+/* comparison_methods (config.py:152-164), as a bit mask */
+enum {
+    NCB_TEST_KS = 1,
+    NCB_TEST_MW = 2,
+    NCB_TEST_TT = 4,
+    NCB_TEST_GMM = 8,
+    NCB_TEST_LOGIT = 16,  /* extension: adds GMM_logit_* (no reference code) */
+    NCB_TEST_AUTO = 32    /* comparisons.py:122-126, 165-167: coverage < 500 -> KS else GMM */
+};
+
+/* cluster_counts (config.py:171, comparisons.py:368-376) */
+enum { NCB_COUNTS_NONE = 0, NCB_COUNTS_HARD = 1, NCB_COUNTS_SOFT = 2 };
+
+/* where a buffer lives */
+enum { NCB_MEM_HOST = 0, NCB_MEM_DEVICE = 1 };
+
+/* input layout */
+enum {
+    NCB_LAYOUT_CSR = 0,   /* ragged: pos_offsets[P+1], signal[E][2], label[E]             */
+    NCB_LAYOUT_DENSE = 1  /* the reference's tensor: signal[P][R][V] with NaN, label[R]   */
+};
+
+/* per-position status bits; the row is dropped by the host mirror when
+ * (status & NCB_POS_DROP_MASK) != 0 */
+enum {
+    NCB_POS_OK = 0,
+    NCB_POS_LOW_COVERAGE = 1,   /* run.py:511-515                                        */
+    NCB_POS_BAD_STD = 2,        /* comparisons.py:108-120: std NaN or 0 after the filter */
+    NCB_POS_TOO_MANY_READS = 4, /* more than NCB_MAX_READS valid reads: ncb_wait fails   */
+    NCB_POS_DROP_MASK = 7,
+    NCB_POS_AUTO_GMM = 256,     /* informational, with NCB_TEST_AUTO: the automatic test of
+                                   this position is GMM (coverage >= 500), else KS       */
+    NCB_POS_MW_EXACT_SKIPPED = 512 /* MW p-value left NaN: SciPy would enumerate the exact null
+                                   distribution (a sample of <= 8 values, no ties) and the
+                                   other sample is too large for the on-chip recurrence  */
+};
+
+typedef struct {
+    int32_t struct_size;        /* sizeof(ncb_opts), for forward compatibility           */
+    int32_t tests;              /* NCB_TEST_* mask                                       */
+    int32_t n_samples;          /* S: sample ids are 0..S-1 (config.py:443-445)          */
+    int32_t depleted_condition; /* condition id of `depleted_condition` (comparisons.py:586-587) */
+    int32_t min_coverage;       /* per condition, on valid intensities (run.py:511-515); 0 = off */
+    int32_t dwell_is_raw;       /* 1: apply log10(dwell + 1e-10) (run.py:573); 0: already done */
+    int32_t cluster_counts;     /* NCB_COUNTS_*                                          */
+    int32_t em_fp64;            /* reserved, must be 1: EM runs in fp64 on the float32
+                                   standardised values (the definition in oracle/gmm.py) */
+    int32_t em_max_iter;        /* 100                                                   */
+    int32_t diagnostics;        /* 1: fill ncb_results.diag_* (integer statistics, GMM parameters) */
+    double em_tol;              /* 1e-3                                                  */
+    double reg_covar;           /* 1e-6                                                  */
+} ncb_opts;
+
+/* label byte of a read: bit 0 = condition id (0/1), bits 1..7 = sample id */
+#define NCB_LABEL(cond, sample) ((uint8_t)(((sample) << 1) | ((cond) & 1)))
+
+typedef struct {
+    int32_t layout;             /* NCB_LAYOUT_*                                          */
+    int32_t memory;             /* NCB_MEM_*: where signal/label/pos_offsets live        */
+    int64_t n_positions;        /* P                                                     */
+    int64_t n_entries;          /* CSR: E = pos_offsets[P]; dense: P*R                   */
+    const int64_t *pos_offsets; /* CSR: [P+1]; dense: NULL                               */
+    const float *signal;        /* CSR: [E][2] {intensity, dwell}; dense: [P][R][V]      */
+    const uint8_t *label;       /* CSR: [E]; dense: [R]                                  */
+    int32_t n_reads;            /* dense: R                                              */
+    int32_t n_vars;             /* dense: V (2, or 3 with the motor-dwell column)        */
+} ncb_batch;
+
+/* rows of ncb_results.pvalues ([NCB_PV_ROWS][P], float64, NaN = not tested) */
+enum {
+    NCB_PV_KS_INTENSITY = 0, NCB_PV_KS_DWELL = 1,
+    NCB_PV_MW_INTENSITY = 2, NCB_PV_MW_DWELL = 3,
+    NCB_PV_TT_INTENSITY = 4, NCB_PV_TT_DWELL = 5,
+    NCB_PV_GMM_CHI2 = 6,
+    NCB_PV_GMM_LOGIT = 7, NCB_PV_GMM_LOGIT_COEF = 8,
+    NCB_PV_ROWS = 9
+};
+
+/* rows of ncb_results.stats ([NCB_ST_ROWS][P], float32): the 12 shift statistics in the
+ * reference's column order (comparisons.py:425-433), then GMM_LOR */
+enum {
+    NCB_ST_C1_MEAN_INTENSITY = 0, NCB_ST_C1_MEAN_DWELL = 1,
+    NCB_ST_C1_MEDIAN_INTENSITY = 2, NCB_ST_C1_MEDIAN_DWELL = 3,
+    NCB_ST_C1_SD_INTENSITY = 4, NCB_ST_C1_SD_DWELL = 5,
+    NCB_ST_C2_MEAN_INTENSITY = 6, NCB_ST_C2_MEAN_DWELL = 7,
+    NCB_ST_C2_MEDIAN_INTENSITY = 8, NCB_ST_C2_MEDIAN_DWELL = 9,
+    NCB_ST_C2_SD_INTENSITY = 10, NCB_ST_C2_SD_DWELL = 11,
+    NCB_ST_GMM_LOR = 12,
+    NCB_ST_ROWS = 13
+};
+
+/* rows of ncb_results.diag_i64 ([NCB_DI_ROWS][P]) -- exact integer statistics */
+enum {
+    NCB_DI_N0_INTENSITY = 0, NCB_DI_N1_INTENSITY = 1,   /* valid reads after the outlier filter */
+    NCB_DI_N0_DWELL = 2, NCB_DI_N1_DWELL = 3,
+    NCB_DI_KS_H_INTENSITY = 4, NCB_DI_KS_H_DWELL = 5,   /* h = max|c0*n1/g - c1*n0/g|            */
+    NCB_DI_MW_U2_INTENSITY = 6, NCB_DI_MW_U2_DWELL = 7, /* 2*U1 (average ranks)                  */
+    NCB_DI_MW_TIE_INTENSITY = 8, NCB_DI_MW_TIE_DWELL = 9, /* sum t^3 - t                          */
+    NCB_DI_CONT_00 = 10, NCB_DI_CONT_01 = 11, NCB_DI_CONT_10 = 12, NCB_DI_CONT_11 = 13,
+    NCB_DI_EM_ITERS = 14, NCB_DI_N_GMM = 15, NCB_DI_N_OUTLIERS = 16,
+    NCB_DI_ROWS = 17
+};
+
+/* rows of ncb_results.diag_f64 ([NCB_DF_ROWS][P]) -- GMM fit */
+enum {
+    NCB_DF_BIC1 = 0, NCB_DF_BIC2 = 1,
+    NCB_DF_W0 = 2,
+    NCB_DF_MU0_X = 3, NCB_DF_MU0_Y = 4, NCB_DF_C0_XX = 5, NCB_DF_C0_XY = 6, NCB_DF_C0_YY = 7,
+    NCB_DF_MU1_X = 8, NCB_DF_MU1_Y = 9, NCB_DF_C1_XX = 10, NCB_DF_C1_XY = 11, NCB_DF_C1_YY = 12,
+    NCB_DF_MEAN2_X = 13, NCB_DF_MEAN2_Y = 14, NCB_DF_STD2_X = 15, NCB_DF_STD2_Y = 16,
+    NCB_DF_ROWS = 17
+};
+
+typedef struct {
+    int32_t memory;        /* NCB_MEM_*: where the arrays below live                      */
+    int32_t reserved;
+    int32_t *status;       /* [P]                 NCB_POS_* bits                          */
+    double *pvalues;       /* [NCB_PV_ROWS][P]                                            */
+    float *stats;          /* [NCB_ST_ROWS][P]                                            */
+    uint32_t *counts;      /* [S][2][P] hard: {<sample>_mod, <sample>_unmod} as uint32
+                              (comparisons.py:513-514); soft: the same slots hold float32 */
+    int64_t *diag_i64;     /* [NCB_DI_ROWS][P] or NULL                                    */
+    double *diag_f64;      /* [NCB_DF_ROWS][P] or NULL                                    */
+} ncb_results;
+
+/* --- lifecycle ------------------------------------------------------------------ */
+
+int ncb_abi_version(void);
+
+/* Fills *opts with the reference's defaults (config.py:196-214): tests = GMM|KS,
+ * n_samples = 4, min_coverage = 30, hard counts, 100 EM iterations, tol 1e-3, reg_covar 1e-6. */
+void ncb_default_opts(ncb_opts *opts);
+
+/* Creates a handle on CUDA device `device`.  Fails (NCB_ERR_CUDA) if there is no
+ * usable GPU: there is no CPU fallback. */
+int ncb_create(ncb_handle **out, int device, const ncb_opts *opts);
+int ncb_set_opts(ncb_handle *h, const ncb_opts *opts);
+void ncb_destroy(ncb_handle *h);
+const char *ncb_last_error(const ncb_handle *h);
+
+/* --- the hot path ----------------------------------------------------------------
+ * ncb_compare: replaces the body of TranscriptComparator.compare_transcript
+ * (comparisons.py:83-137) plus Worker._filter_low_cov_positions / the log10 of
+ * _prepare_data (run.py:511-515, 573) for a batch of positions.
+ *
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  With
+ * NCB_MEM_HOST buffers the call copies inputs host->device and results device->host
+ * on that stream (use pinned memory for the copies to be asynchronous) and returns
+ * after enqueueing; ncb_wait() blocks until the results are in place.  With
+ * NCB_MEM_DEVICE buffers nothing is copied and the kernels are only enqueued.        */
+int ncb_compare(ncb_handle *h, const ncb_batch *batch, ncb_results *results, void *stream);
+int ncb_wait(ncb_handle *h, void *stream);
+
+/* --- unit entry points (each is one stage of ncb_compare, exposed for parity tests) */
+
+/* Exact two-sided two-sample KS p-values from integer statistics: replaces
+ * scipy.stats._stats_py._attempt_exact_2kssamp (scipy/stats/_stats_py.py:7825-7870),
+ * reached from comparisons.py:222 via scipy.stats.mstats.ks_twosamp.  n0,n1,h: [n].  */
+int ncb_ks_exact_pvalues(ncb_handle *h, int64_t n, const int32_t *n0, const int32_t *n1,
+                         const int64_t *hstat, double *p_out, int memory, void *stream);
+
+/* Benjamini-Hochberg q-values ignoring NaNs: replaces
+ * Postprocessor._multipletests_filter_nan (postprocessing.py:255-285).
+ * scale multiplies every q (postprocessing.py:232-235 uses N/n for auto_qvalue); 1.0 otherwise. */
+int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
+               int memory, void *stream);
+
+/* --- introspection ---------------------------------------------------------------- */
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t ncb_kernel_launches(const ncb_handle *h);
+/* Device milliseconds of the position kernels / KS p-value kernels of the last ncb_compare
+ * whose batch was timed (set NCB_TIMING=1 in the environment or call ncb_set_timing). */
+int ncb_set_timing(ncb_handle *h, int enabled);
+int ncb_last_timing(ncb_handle *h, float *ms_position_kernels, float *ms_ks_kernels, float *ms_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCB_H */

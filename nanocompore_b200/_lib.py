@@ -1,0 +1,123 @@
+"""
+ctypes binding of libncb.so (include/ncb.h).  This is the only way the Python host code
+reaches the CUDA kernels; there is no CPU fallback -- if the library cannot be loaded, or
+there is no GPU, every compute entry point raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libncb.so')
+
+NCB_ABI_VERSION = 1
+NCB_MAX_READS = 10240
+NCB_MAX_SAMPLES = 64
+
+NCB_OK, NCB_ERR_INVALID, NCB_ERR_CUDA, NCB_ERR_NOMEM, NCB_ERR_TOO_MANY_READS = 0, -1, -2, -3, -4
+
+NCB_TEST_KS, NCB_TEST_MW, NCB_TEST_TT, NCB_TEST_GMM, NCB_TEST_LOGIT, NCB_TEST_AUTO = 1, 2, 4, 8, 16, 32
+NCB_COUNTS_NONE, NCB_COUNTS_HARD, NCB_COUNTS_SOFT = 0, 1, 2
+NCB_MEM_HOST, NCB_MEM_DEVICE = 0, 1
+NCB_LAYOUT_CSR, NCB_LAYOUT_DENSE = 0, 1
+
+NCB_POS_LOW_COVERAGE, NCB_POS_BAD_STD, NCB_POS_TOO_MANY_READS = 1, 2, 4
+NCB_POS_DROP_MASK = 7
+NCB_POS_AUTO_GMM = 256
+NCB_POS_MW_EXACT_SKIPPED = 512
+
+PV = dict(KS_INTENSITY=0, KS_DWELL=1, MW_INTENSITY=2, MW_DWELL=3, TT_INTENSITY=4, TT_DWELL=5,
+          GMM_CHI2=6, GMM_LOGIT=7, GMM_LOGIT_COEF=8)
+NCB_PV_ROWS = 9
+ST = dict(C1_MEAN_INTENSITY=0, C1_MEAN_DWELL=1, C1_MEDIAN_INTENSITY=2, C1_MEDIAN_DWELL=3,
+          C1_SD_INTENSITY=4, C1_SD_DWELL=5, C2_MEAN_INTENSITY=6, C2_MEAN_DWELL=7,
+          C2_MEDIAN_INTENSITY=8, C2_MEDIAN_DWELL=9, C2_SD_INTENSITY=10, C2_SD_DWELL=11, GMM_LOR=12)
+NCB_ST_ROWS = 13
+DI = dict(N0_INTENSITY=0, N1_INTENSITY=1, N0_DWELL=2, N1_DWELL=3, KS_H_INTENSITY=4, KS_H_DWELL=5,
+          MW_U2_INTENSITY=6, MW_U2_DWELL=7, MW_TIE_INTENSITY=8, MW_TIE_DWELL=9,
+          CONT_00=10, CONT_01=11, CONT_10=12, CONT_11=13, EM_ITERS=14, N_GMM=15, N_OUTLIERS=16)
+NCB_DI_ROWS = 17
+DF = dict(BIC1=0, BIC2=1, W0=2, MU0_X=3, MU0_Y=4, C0_XX=5, C0_XY=6, C0_YY=7,
+          MU1_X=8, MU1_Y=9, C1_XX=10, C1_XY=11, C1_YY=12,
+          MEAN2_X=13, MEAN2_Y=14, STD2_X=15, STD2_Y=16)
+NCB_DF_ROWS = 17
+
+EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
+           'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
+           'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing']
+
+
+class NcbOpts(C.Structure):
+    _fields_ = [('struct_size', C.c_int32), ('tests', C.c_int32), ('n_samples', C.c_int32),
+                ('depleted_condition', C.c_int32), ('min_coverage', C.c_int32),
+                ('dwell_is_raw', C.c_int32), ('cluster_counts', C.c_int32), ('em_fp64', C.c_int32),
+                ('em_max_iter', C.c_int32), ('diagnostics', C.c_int32),
+                ('em_tol', C.c_double), ('reg_covar', C.c_double)]
+
+
+class NcbBatch(C.Structure):
+    _fields_ = [('layout', C.c_int32), ('memory', C.c_int32), ('n_positions', C.c_int64),
+                ('n_entries', C.c_int64), ('pos_offsets', C.c_void_p), ('signal', C.c_void_p),
+                ('label', C.c_void_p), ('n_reads', C.c_int32), ('n_vars', C.c_int32)]
+
+
+class NcbResults(C.Structure):
+    _fields_ = [('memory', C.c_int32), ('reserved', C.c_int32), ('status', C.c_void_p),
+                ('pvalues', C.c_void_p), ('stats', C.c_void_p), ('counts', C.c_void_p),
+                ('diag_i64', C.c_void_p), ('diag_f64', C.c_void_p)]
+
+
+class NcbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libncb error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Loads libncb.so (built in-tree by ``python -m nanocompore_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m nanocompore_b200.build` "
+            "(nanocompore_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.ncb_abi_version.restype = C.c_int
+    lib.ncb_default_opts.argtypes = [C.POINTER(NcbOpts)]
+    lib.ncb_default_opts.restype = None
+    lib.ncb_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(NcbOpts)]
+    lib.ncb_create.restype = C.c_int
+    lib.ncb_set_opts.argtypes = [vp, C.POINTER(NcbOpts)]
+    lib.ncb_set_opts.restype = C.c_int
+    lib.ncb_destroy.argtypes = [vp]
+    lib.ncb_destroy.restype = None
+    lib.ncb_last_error.argtypes = [vp]
+    lib.ncb_last_error.restype = C.c_char_p
+    lib.ncb_compare.argtypes = [vp, C.POINTER(NcbBatch), C.POINTER(NcbResults), vp]
+    lib.ncb_compare.restype = C.c_int
+    lib.ncb_wait.argtypes = [vp, vp]
+    lib.ncb_wait.restype = C.c_int
+    lib.ncb_ks_exact_pvalues.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, vp]
+    lib.ncb_ks_exact_pvalues.restype = C.c_int
+    lib.ncb_bh_fdr.argtypes = [vp, i64, vp, vp, C.c_double, C.c_int, vp]
+    lib.ncb_bh_fdr.restype = C.c_int
+    lib.ncb_kernel_launches.argtypes = [vp]
+    lib.ncb_kernel_launches.restype = i64
+    lib.ncb_set_timing.argtypes = [vp, C.c_int]
+    lib.ncb_set_timing.restype = C.c_int
+    lib.ncb_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.ncb_last_timing.restype = C.c_int
+    if lib.ncb_abi_version() != NCB_ABI_VERSION:
+        raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
+    _lib = lib
+    return lib
+
+
+def default_opts():
+    o = NcbOpts()
+    load().ncb_default_opts(C.byref(o))
+    return o

@@ -1,0 +1,349 @@
+"""
+Drop-in mirror of the reference's ``nanocompore/comparisons.py`` for the per-position
+two-condition comparison, running on the B200 kernels of libncb.
+
+Same names, signatures, config getters, result columns and error behaviour as the reference
+(/root/reference/nanocompore/comparisons.py):
+
+  * ``TranscriptComparator(config, worker, random_seed=42, dtype=torch.float32)``   :29-38
+  * ``TranscriptComparator.compare_transcript(transcript, data, samples, conditions,
+    positions, device) -> (transcript, DataFrame | None)``                          :41-148
+  * module helpers ``nanstd``, ``calculate_lors``, ``get_contingency_matrices``,
+    ``get_soft_contingency_matrices``, ``cross_corr_matrix``, ``harmomic_series``,
+    ``combine_pvalues_hou``                                                         :622-744
+
+What differs underneath: the reference walks the positions in Python and calls torch / SciPy /
+gmm_gpu per position; here the whole tensor goes through ONE libncb call (shift statistics,
+outlier filter, standardisation, KS / MW / TT, both Gaussian mixtures, contingency, counts,
+LOR, chi-squared) and this module only assembles the DataFrame.  There is no CPU fallback:
+with no GPU or no libncb.so the constructor's first use raises.
+
+Not supported (raises NotImplementedError): ``motor_dwell_offset > 0`` (3-variable GMM,
+SURVEY 8f N4) and the ``GOF`` test (out of scope).
+"""
+import numpy as np
+import pandas as pd
+import torch
+
+from nanocompore_b200 import _lib as L
+from nanocompore_b200.engine import Engine, Results, make_labels, tests_mask
+
+INTENSITY = 0
+DWELL = 1
+MOTOR = 2
+
+HARD_ASSIGNMENT = 'hard'
+SOFT_ASSIGNMENT = 'soft'
+
+SHIFT_COLUMNS = [(f"c{c + 1}_{stat}_{dim}", L.ST[f"C{c + 1}_{stat.upper()}_{dim.upper()}"])
+                 for c in (0, 1) for stat in ('mean', 'median', 'sd') for dim in ('intensity', 'dwell')]
+
+_NONPARAMETRIC = {'KS': ('KS_INTENSITY', 'KS_DWELL'), 'MW': ('MW_INTENSITY', 'MW_DWELL'),
+                  'TT': ('TT_INTENSITY', 'TT_DWELL')}
+_AUTO_PVALUE = {'KS': 'KS_intensity_pvalue', 'GMM': 'GMM_chi2_pvalue'}
+
+
+class NanocomporeError(Exception):
+    """Same role as nanocompore.common.NanocomporeError."""
+
+
+class TranscriptComparator:
+    """
+    Compare a set of positions (reference: comparisons.py:29-619).
+    """
+
+    def __init__(self, config, worker, random_seed=42, dtype=torch.float32, with_logit=False):
+        self._config = config
+        # The reference seeds gmm_gpu's random initialisation; this implementation initialises
+        # the mixtures deterministically (oracle/gmm.py), so the seed is accepted and unused.
+        self._random_seed = random_seed
+        self._dtype = dtype
+        self._motor_dwell_offset = self._config.get_motor_dwell_offset()
+        self._worker = worker
+        self._with_logit = with_logit
+        self._engines = {}
+
+    # ------------------------------------------------------------------ engine
+    def _engine(self, device):
+        """One libncb handle per CUDA device, created on first use (no CUDA work at import or
+        construction time, so fork and spawn start methods both work: run.py:364-372)."""
+        if isinstance(device, str) and device.startswith('cuda'):
+            dev = torch.device(device)
+            index = dev.index if dev.index is not None else 0
+        else:
+            # the reference's 'cpu' device string: this implementation has no CPU path
+            index = 0
+        if index not in self._engines:
+            methods = [m for m in self._config.get_comparison_methods()]
+            for m in methods:
+                if m.upper() == 'GOF':
+                    raise NotImplementedError("Test GOF is not implemented!")
+            self._engines[index] = Engine(
+                index,
+                tests=tests_mask(methods, self._with_logit),
+                n_samples=max(self._config.get_sample_ids().values()) + 1,
+                depleted_condition=self._depleted_condition_id(),
+                min_coverage=0,            # Worker._filter_low_cov_positions already ran
+                dwell_is_raw=False,        # Worker._prepare_data already took the log10
+                cluster_counts=self._config.get_cluster_counts())
+        return self._engines[index]
+
+    def _depleted_condition_id(self):
+        depleted = self._config.get_depleted_condition()
+        return int(self._config.get_condition_ids()[depleted])
+
+    # ------------------------------------------------------------------ the hot path
+    def compare_transcript(self, transcript, data, samples, conditions, positions, device):
+        """
+        Compare the two conditions for the given transcript (comparisons.py:41-148).
+
+        data: (positions, reads, vars) float tensor, NaN = missing; samples, conditions: (reads,);
+        positions: (positions,).  Returns (transcript, DataFrame) or (transcript, None) when
+        there are no positions.
+        """
+        n_positions = len(positions)
+        if n_positions == 0:
+            return (transcript, None)
+        if self._motor_dwell_offset > 0 or data.shape[2] != 2:
+            raise NotImplementedError(
+                "motor_dwell_offset > 0 (3-variable GMM) is not implemented in nanocompore_b200")
+
+        engine = self._engine(device)
+        pos_host = positions.cpu() if isinstance(positions, torch.Tensor) else torch.as_tensor(positions)
+        results = pd.DataFrame({'transcript_id': transcript.id, 'pos': pos_host})
+
+        self._worker.log("trace", "Start comparison kernels")
+        dev_data = torch.as_tensor(data).to(device=engine.device, dtype=torch.float32).contiguous()
+        labels = torch.from_numpy(make_labels(_to_numpy(samples), _to_numpy(conditions))).to(engine.device)
+        res = engine.compare_dense(dev_data, labels).numpy()
+        status, pv, st, counts = res['status'], res['pvalues'], res['stats'], res['counts']
+        if (status & L.NCB_POS_TOO_MANY_READS).any():
+            raise NanocomporeError(
+                f"A position of transcript {transcript.name} has more than {L.NCB_MAX_READS} reads; "
+                "lower downsample_high_coverage")
+
+        for column, row in SHIFT_COLUMNS:
+            results[column] = st[row]
+
+        # comparisons.py:108-120
+        bad_stds = (status & L.NCB_POS_BAD_STD) != 0
+        if bad_stds.any():
+            self._worker.log(
+                "warning",
+                "The standard deviation cannot be calculated for some positions on "
+                f"transcript {transcript.name}, but are required for scaling the data. "
+                f"The positions {pos_host[torch.from_numpy(bad_stds)].tolist()} will be skipped.")
+            results.drop(np.arange(results.shape[0])[bad_stds], inplace=True, axis=0)
+        keep = ~bad_stds
+        n_positions = int(keep.sum())
+        status, pv, st, counts = status[keep], pv[:, keep], st[:, keep], counts[:, :, keep]
+
+        methods = list(self._config.get_comparison_methods())
+        has_auto = 'auto' in methods
+        auto_test_mask = None
+        if has_auto:
+            auto_test_mask = np.where((status & L.NCB_POS_AUTO_GMM) != 0, 'GMM', 'KS')
+        for test, mask in self._get_test_masks(auto_test_mask, n_positions).items():
+            test_results = self._test_columns(test, pv, st, counts, status, transcript)
+            self._merge_results(results, test_results, test, mask, auto_test_mask, n_positions)
+
+        context = self._config.get_sequence_context()
+        if context > 0:
+            tests = [col for col in results.columns if 'pvalue' in col]
+            for test in tests:
+                results[f"{test}_context_{context}"] = self._combine_context_pvalues(results, test)
+
+        return transcript, results
+
+    def _get_test_masks(self, auto_test_mask, n_positions):
+        # comparisons.py:150-162; iteration order is the config order (the reference iterates
+        # a set, so its column order between tests is not defined)
+        methods = list(dict.fromkeys(self._config.get_comparison_methods()))
+        base_tests = [m for m in methods if m != 'auto']
+        masks = {test: np.ones(n_positions, dtype=bool) for test in base_tests}
+        if auto_test_mask is not None:
+            for test in sorted(set(auto_test_mask) - set(base_tests)):
+                masks[test] = auto_test_mask == test
+        return masks
+
+    def _test_columns(self, test, pv, st, counts, status, transcript):
+        """Result columns of one test over all kept positions (what ``_run_test`` returns)."""
+        key = test.upper()
+        if key in _NONPARAMETRIC:
+            a, b = _NONPARAMETRIC[key]
+            if key == 'MW' and (status & L.NCB_POS_MW_EXACT_SKIPPED).any():
+                self._worker.log("error", "Error in nonparametric test: exact Mann-Whitney "
+                                 f"distribution too large on transcript {transcript.name}")
+            return {f'{test}_intensity_pvalue': pv[L.PV[a]].copy(),
+                    f'{test}_dwell_pvalue': pv[L.PV[b]].copy()}
+        if key == 'GMM':
+            out = {'GMM_chi2_pvalue': pv[L.PV['GMM_CHI2']].copy(),
+                   'GMM_LOR': st[L.ST['GMM_LOR']].copy()}
+            if self._with_logit:
+                out['GMM_logit_pvalue'] = pv[L.PV['GMM_LOGIT']].copy()
+                out['GMM_logit_coef'] = pv[L.PV['GMM_LOGIT_COEF']].copy()
+            mode = self._config.get_cluster_counts()
+            if mode in (HARD_ASSIGNMENT, SOFT_ASSIGNMENT):
+                for label, sid in self._config.get_sample_ids().items():
+                    mod, unmod = counts[sid, 0], counts[sid, 1]
+                    if mode == SOFT_ASSIGNMENT:
+                        mod, unmod = mod.view(np.float32), unmod.view(np.float32)
+                    else:
+                        mod, unmod = mod.astype(np.uint32), unmod.astype(np.uint32)
+                    out[f'{label}_mod'] = mod.copy()
+                    out[f'{label}_unmod'] = unmod.copy()
+            return out
+        raise NotImplementedError(f"Test {test} is not implemented!")
+
+    def _merge_results(self, results, test_results, test, mask, auto_test_mask, n_positions):
+        # comparisons.py:204-215
+        has_auto = 'auto' in self._config.get_comparison_methods()
+        if has_auto and 'auto_pvalue' not in results:
+            results['auto_pvalue'] = np.full(n_positions, np.nan)
+            results['auto_test'] = auto_test_mask
+        for column, values in test_results.items():
+            if mask.all():
+                results[column] = values
+            else:
+                results.loc[mask, column] = values[mask]
+            if has_auto and column == _AUTO_PVALUE.get(test):
+                rows = auto_test_mask == test
+                results.loc[rows, 'auto_pvalue'] = results.loc[rows, column]
+
+    def _combine_context_pvalues(self, results, test):
+        # comparisons.py:436-474 (host side)
+        context = self._config.get_sequence_context()
+        if self._config.get_sequence_context_weights() == "harmonic":
+            weights = harmomic_series(context)
+        else:
+            weights = [1] * (2 * context + 1)
+        pos = results.pos.to_numpy().astype(np.int64)
+        idx = pos - pos.min()
+        padded = np.ones(int(idx.max()) + 1 + 2 * context, dtype=float)
+        padded[idx + context] = results[test].to_numpy(dtype=float)
+        corr = cross_corr_matrix(padded[context:-context], context)
+        windows = np.lib.stride_tricks.sliding_window_view(padded, 2 * context + 1)
+        combined = np.full(windows.shape[0], np.nan)
+        for i, window in enumerate(windows):
+            if not np.isnan(window[context]):
+                combined[i] = combine_pvalues_hou(np.nan_to_num(window, nan=1), weights, corr)
+        return combined[idx]
+
+    def retry(self, fn, delay=5, backoff=5, max_attempts=3, exception=Exception):
+        # comparisons.py:608-619; libncb sizes its scratch per batch, so OOM is not expected
+        import time
+        for attempt in range(1, max_attempts):
+            try:
+                return fn()
+            except exception as e:
+                self._worker.log("warning", f"Got error {e} on attempt {attempt}/{max_attempts}")
+                time.sleep(delay)
+                delay += backoff
+        return fn()
+
+
+def _to_numpy(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+# ---------------------------------------------------------------------------------------
+# Module-level helpers the reference exports (tests/test_comparisons.py:9-12, plotting.py:22).
+# Small host-side tensor utilities: kept for API compatibility; compare_transcript does not
+# use them (the kernels compute the same quantities per position).
+# ---------------------------------------------------------------------------------------
+
+def nanstd(X, dim):
+    """Population standard deviation ignoring NaNs (comparisons.py:622-624)."""
+    count = (~torch.isnan(X)).sum(dim)
+    centred = X - X.nanmean(dim).unsqueeze(1)
+    return torch.sqrt(torch.nansum(centred * centred, dim) / count)
+
+
+def calculate_lors(contingencies):
+    """log odds ratio of each 2x2 table, rounded to 3 decimals (comparisons.py:708-711)."""
+    odds = contingencies[:, :, 0] / contingencies[:, :, 1]
+    return torch.round(torch.log(odds[:, 0] / odds[:, 1]), decimals=3)
+
+
+def get_contingency_matrices(conditions, predictions):
+    """(positions, 2, 2) counts of condition x predicted cluster; NaN predictions never match
+    (comparisons.py:714-729)."""
+    cond = conditions.unsqueeze(0)
+    tables = torch.zeros((predictions.shape[0], 2, 2))
+    for c in (0, 1):
+        for k in (0, 1):
+            tables[:, c, k] = ((cond == c) & (predictions == k)).sum(1)
+    return tables
+
+
+def get_soft_contingency_matrices(conditions, cluster_probs):
+    """(positions, 2, 2) sums of posteriors per condition (comparisons.py:732-744)."""
+    tables = torch.zeros((cluster_probs.shape[0], 2, 2))
+    for c in (0, 1):
+        tables[:, c, :] = cluster_probs[:, conditions == c, :].nansum(1)
+    return tables
+
+
+def harmomic_series(sequence_context):
+    """Symmetric harmonic weights 1/(|i|+1) (comparisons.py:654-656; the reference's spelling)."""
+    return [1 / (abs(i) + 1) for i in range(-sequence_context, sequence_context + 1)]
+
+
+def cross_corr_matrix(pvalues, context=2):
+    """Correlation of the p-value track with its own shifts by -context..context
+    (comparisons.py:627-651)."""
+    pvalues = np.asarray(pvalues, dtype=float)
+    if len(pvalues) < 3 * context + 3:
+        raise RuntimeError("Not enough p-values for a context of order %s" % context)
+    pvalues = np.nan_to_num(pvalues, nan=1)
+    if (pvalues == 0).any() or np.isinf(pvalues).any() or (pvalues > 1).any():
+        raise RuntimeError("At least one p-value is invalid")
+    width = 2 * context + 1
+    if (pvalues == 1).all():
+        return np.ones((width, width))
+    size = pvalues.size
+    shifted = [np.roll(pvalues, s)[context:size - context] for s in range(-context, context + 1)]
+    matrix = np.zeros((width, width))
+    for x in range(width):
+        for y in range(x + 1):
+            matrix[x, y] = matrix[y, x] = np.corrcoef(shifted[x], shifted[y])[0, 1]
+    return matrix
+
+
+def combine_pvalues_hou(pvalues, weights, cor_mat):
+    """Hou's approximation for a weighted Fisher combination of dependent p-values
+    (comparisons.py:659-705; https://doi.org/10.1016/j.spl.2004.11.028)."""
+    from scipy.stats import chi2
+    if len(pvalues) != len(weights):
+        raise ValueError("Can't combine pvalues if pvalues and weights are not the same length.")
+    if cor_mat.shape[0] != cor_mat.shape[1] or cor_mat.shape[0] != len(pvalues):
+        raise ValueError("The correlation matrix needs to be square, with each"
+                         "dimension equal to the length of the pvalued vector.")
+    p = np.asarray(pvalues, dtype=np.float64)
+    w = np.asarray(weights, dtype=np.float64)
+    if (p == 1).all():
+        return 1
+    if (p == 0).any() or np.isinf(p).any() or (p > 1).any():
+        raise ValueError("At least one p-value is invalid")
+    k = len(p)
+    # covariance of -2 ln p terms, Kost & McDermott eq. 8
+    cov_sum = np.float64(0)
+    for i in range(k):
+        for j in range(i + 1, k):
+            r = cor_mat[i][j]
+            cov_sum += w[i] * w[j] * ((3.263 * r) + (0.710 * r ** 2) + (0.027 * r ** 3))
+    sw_sum = np.float64(0)
+    w_sum = np.float64(0)
+    tau = np.float64(0)
+    for i in range(k):
+        sw_sum += w[i] ** 2
+        w_sum += w[i]
+        tau += w[i] * (-2 * np.log(p[i]))
+    scale = (2 * sw_sum + cov_sum) / (2 * w_sum)
+    dof = (4 * w_sum ** 2) / (2 * sw_sum + cov_sum)
+    combined = chi2.sf(tau / scale, dof)
+    if combined == 0:
+        combined = np.finfo(np.float64).tiny
+    return combined

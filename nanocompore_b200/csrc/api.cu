@@ -1,0 +1,443 @@
+// libncb C ABI (include/ncb.h): handle lifecycle, buffer staging, kernel sequencing.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include "ncb_internal.h"
+
+int ncb_configure_ks_kernels(void);
+
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct ncb_handle {
+    int device = 0;
+    int sm_count = 148;
+    ncb_opts opts;
+    std::string err;
+    int64_t launches = 0;
+    int timing = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    // grow-only device buffers
+    DevBuf in_signal, in_label, in_offsets;
+    DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
+    DevBuf ks_n0, ks_n1, ks_h;
+    DevBuf wl_count, wl_list;
+    DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch;
+    DevBuf fdr_scratch, fdr_p, fdr_q;
+    DevBuf unit_a, unit_b, unit_c, unit_d;
+};
+
+static int fail(ncb_handle *h, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (h) {
+        h->err = what;
+        if (e != cudaSuccess) {
+            h->err += ": ";
+            h->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CK(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            cudaGetLastError();                                                      \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? NCB_ERR_NOMEM : NCB_ERR_CUDA, #call, e_); \
+        }                                                                            \
+    } while (0)
+
+static int ensure(ncb_handle *h, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 256;
+    if (b.bytes >= bytes) return NCB_OK;
+    if (b.ptr) {
+        cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8;   // a little slack: batches of similar size do not realloc
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.ptr, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.ptr = nullptr;
+        return fail(h, NCB_ERR_NOMEM, "cudaMalloc", e);
+    }
+    b.bytes = want;
+    return NCB_OK;
+}
+#define ENSURE(buf, bytes)                         \
+    do {                                           \
+        int r_ = ensure(h, (buf), (bytes));        \
+        if (r_ != NCB_OK) return r_;               \
+    } while (0)
+
+static void release(DevBuf &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+}
+
+extern "C" {
+
+int ncb_abi_version(void) { return NCB_ABI_VERSION; }
+
+void ncb_default_opts(ncb_opts *o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->struct_size = (int32_t)sizeof(ncb_opts);
+    o->tests = NCB_TEST_GMM | NCB_TEST_KS;
+    o->n_samples = 4;
+    o->depleted_condition = 0;
+    o->min_coverage = 30;
+    o->dwell_is_raw = 0;
+    o->cluster_counts = NCB_COUNTS_HARD;
+    o->em_fp64 = 1;
+    o->em_max_iter = 100;
+    o->diagnostics = 0;
+    o->em_tol = 1e-3;
+    o->reg_covar = 1e-6;
+}
+
+static int check_opts(ncb_handle *h, const ncb_opts *o) {
+    if (!o || o->struct_size != (int32_t)sizeof(ncb_opts)) return fail(h, NCB_ERR_INVALID, "ncb_opts: bad struct_size");
+    if (o->n_samples < 0 || o->n_samples > NCB_MAX_SAMPLES) return fail(h, NCB_ERR_INVALID, "ncb_opts: n_samples out of range");
+    if (o->depleted_condition != 0 && o->depleted_condition != 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: depleted_condition must be 0 or 1");
+    if (o->em_max_iter < 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: em_max_iter < 1");
+    if (o->cluster_counts < NCB_COUNTS_NONE || o->cluster_counts > NCB_COUNTS_SOFT) return fail(h, NCB_ERR_INVALID, "ncb_opts: cluster_counts");
+    return NCB_OK;
+}
+
+int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
+    if (!out) return NCB_ERR_INVALID;
+    *out = nullptr;
+    ncb_handle *h = new ncb_handle();
+    ncb_opts def;
+    ncb_default_opts(&def);
+    h->opts = opts ? *opts : def;
+    int r = check_opts(h, &h->opts);
+    if (r != NCB_OK) { delete h; return r; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        fprintf(stderr, "libncb: no usable CUDA device %d (%s); there is no CPU fallback\n", device,
+                e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        delete h;
+        return NCB_ERR_CUDA;
+    }
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return NCB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return NCB_ERR_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    if (ncb_configure_kernels() != 0 || ncb_configure_ks_kernels() != 0) {
+        fprintf(stderr, "libncb: kernel configuration failed on device %d (%s): built for sm_100a\n",
+                device, cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return NCB_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+    const char *t = getenv("NCB_TIMING");
+    h->timing = (t && t[0] == '1') ? 1 : 0;
+    *out = h;
+    return NCB_OK;
+}
+
+int ncb_set_opts(ncb_handle *h, const ncb_opts *opts) {
+    if (!h) return NCB_ERR_INVALID;
+    int r = check_opts(h, opts);
+    if (r != NCB_OK) return r;
+    h->opts = *opts;
+    return NCB_OK;
+}
+
+void ncb_destroy(ncb_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
+                     &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
+                     &h->ks_h, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
+                     &h->kw_bin, &h->kw_fetch, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
+                     &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d};
+    for (DevBuf *b : all) release(*b);
+    for (int i = 0; i < 4; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+}
+
+const char *ncb_last_error(const ncb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+static int ks_work(ncb_handle *h, int64_t nprob, NcbKsWork &w) {
+    ENSURE(h->kw_hist, (NCB_KS_NBINS + 1) * sizeof(int32_t));
+    ENSURE(h->kw_cursor, NCB_KS_NBINS * sizeof(int32_t));
+    ENSURE(h->kw_list, (size_t)nprob * sizeof(int32_t));
+    ENSURE(h->kw_bin, (size_t)nprob);
+    ENSURE(h->kw_fetch, NCB_KS_KINDS * sizeof(int32_t));
+    w.hist = (int32_t *)h->kw_hist.ptr;
+    w.cursor = (int32_t *)h->kw_cursor.ptr;
+    w.list = (int32_t *)h->kw_list.ptr;
+    w.bin = (uint8_t *)h->kw_bin.ptr;
+    w.fetch = (int32_t *)h->kw_fetch.ptr;
+    return NCB_OK;
+}
+
+int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *stream) {
+    if (!h) return NCB_ERR_INVALID;
+    if (!b || !res) return fail(h, NCB_ERR_INVALID, "ncb_compare: null batch or results");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t P = b->n_positions;
+    if (P < 0 || P > 0x7fffffffLL / 2) return fail(h, NCB_ERR_INVALID, "ncb_compare: n_positions out of range");
+    if (P == 0) return NCB_OK;
+    if (!res->status || !res->pvalues || !res->stats) return fail(h, NCB_ERR_INVALID, "ncb_compare: status, pvalues and stats are required");
+    if (!b->signal || !b->label) return fail(h, NCB_ERR_INVALID, "ncb_compare: null signal or label");
+    CK(cudaSetDevice(h->device));
+    const ncb_opts &o = h->opts;
+    const bool csr = b->layout == NCB_LAYOUT_CSR;
+    int64_t E;
+    size_t label_bytes;
+    int n_vars;
+    if (csr) {
+        if (!b->pos_offsets) return fail(h, NCB_ERR_INVALID, "ncb_compare: CSR batch without pos_offsets");
+        E = b->n_entries;
+        if (E < 0) return fail(h, NCB_ERR_INVALID, "ncb_compare: negative n_entries");
+        label_bytes = (size_t)E;
+        n_vars = 2;
+    } else if (b->layout == NCB_LAYOUT_DENSE) {
+        if (b->n_reads < 0 || b->n_vars < 2 || b->n_vars > 3) return fail(h, NCB_ERR_INVALID, "ncb_compare: dense batch needs n_reads >= 0 and 2 <= n_vars <= 3");
+        E = P * (int64_t)b->n_reads;
+        label_bytes = (size_t)b->n_reads;
+        n_vars = b->n_vars;
+    } else {
+        return fail(h, NCB_ERR_INVALID, "ncb_compare: unknown layout");
+    }
+    const size_t signal_bytes = (size_t)E * n_vars * sizeof(float);
+    const int S = o.n_samples;
+
+    NcbDeviceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_positions = P;
+    a.n_reads = csr ? 0 : b->n_reads;
+    a.n_vars = n_vars;
+    a.tests = o.tests;
+    a.n_samples = S;
+    a.depleted_condition = o.depleted_condition;
+    a.min_coverage = o.min_coverage;
+    a.dwell_is_raw = o.dwell_is_raw;
+    a.cluster_counts = o.cluster_counts;
+    a.em_max_iter = o.em_max_iter;
+    a.em_tol = o.em_tol;
+    a.reg_covar = o.reg_covar;
+
+    const bool time_it = h->timing != 0;
+    if (time_it) CK(cudaEventRecord(h->ev[0], s));
+
+    // ---- inputs ------------------------------------------------------------------------
+    if (b->memory == NCB_MEM_HOST) {
+        ENSURE(h->in_signal, signal_bytes);
+        ENSURE(h->in_label, label_bytes);
+        CK(cudaMemcpyAsync(h->in_signal.ptr, b->signal, signal_bytes, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->in_label.ptr, b->label, label_bytes, cudaMemcpyHostToDevice, s));
+        a.signal = (const float *)h->in_signal.ptr;
+        a.label = (const uint8_t *)h->in_label.ptr;
+        if (csr) {
+            ENSURE(h->in_offsets, (size_t)(P + 1) * sizeof(int64_t));
+            CK(cudaMemcpyAsync(h->in_offsets.ptr, b->pos_offsets, (size_t)(P + 1) * sizeof(int64_t),
+                               cudaMemcpyHostToDevice, s));
+            a.pos_offsets = (const int64_t *)h->in_offsets.ptr;
+        }
+    } else if (b->memory == NCB_MEM_DEVICE) {
+        a.signal = b->signal;
+        a.label = b->label;
+        a.pos_offsets = csr ? b->pos_offsets : nullptr;
+    } else {
+        return fail(h, NCB_ERR_INVALID, "ncb_compare: unknown batch memory kind");
+    }
+
+    // ---- outputs -----------------------------------------------------------------------
+    const size_t b_status = (size_t)P * sizeof(int32_t);
+    const size_t b_pv = (size_t)P * NCB_PV_ROWS * sizeof(double);
+    const size_t b_st = (size_t)P * NCB_ST_ROWS * sizeof(float);
+    const size_t b_cnt = (size_t)P * S * 2 * sizeof(uint32_t);
+    const size_t b_di = (size_t)P * NCB_DI_ROWS * sizeof(int64_t);
+    const size_t b_df = (size_t)P * NCB_DF_ROWS * sizeof(double);
+    const bool out_host = res->memory == NCB_MEM_HOST;
+    if (!out_host && res->memory != NCB_MEM_DEVICE) return fail(h, NCB_ERR_INVALID, "ncb_compare: unknown results memory kind");
+    if (out_host) {
+        ENSURE(h->out_status, b_status);
+        ENSURE(h->out_pvalues, b_pv);
+        ENSURE(h->out_stats, b_st);
+        a.status = (int32_t *)h->out_status.ptr;
+        a.pvalues = (double *)h->out_pvalues.ptr;
+        a.stats = (float *)h->out_stats.ptr;
+        if (res->counts && S > 0) { ENSURE(h->out_counts, b_cnt); a.counts = (uint32_t *)h->out_counts.ptr; }
+        if (res->diag_i64) { ENSURE(h->out_di, b_di); a.diag_i64 = (int64_t *)h->out_di.ptr; }
+        if (res->diag_f64) { ENSURE(h->out_df, b_df); a.diag_f64 = (double *)h->out_df.ptr; }
+    } else {
+        a.status = res->status;
+        a.pvalues = res->pvalues;
+        a.stats = res->stats;
+        a.counts = S > 0 ? res->counts : nullptr;
+        a.diag_i64 = res->diag_i64;
+        a.diag_f64 = res->diag_f64;
+    }
+
+    // ---- scratch -----------------------------------------------------------------------
+    ENSURE(h->ks_n0, (size_t)P * 2 * sizeof(int32_t));
+    ENSURE(h->ks_n1, (size_t)P * 2 * sizeof(int32_t));
+    ENSURE(h->ks_h, (size_t)P * 2 * sizeof(int64_t));
+    a.ks_n0 = (int32_t *)h->ks_n0.ptr;
+    a.ks_n1 = (int32_t *)h->ks_n1.ptr;
+    a.ks_h = (int64_t *)h->ks_h.ptr;
+    ENSURE(h->wl_count, NCB_NUM_CLASSES * sizeof(int32_t));
+    ENSURE(h->wl_list, (size_t)P * NCB_NUM_CLASSES * sizeof(int32_t));
+    NcbWorklists wl;
+    wl.class_count = (int32_t *)h->wl_count.ptr;
+    wl.class_list = (int32_t *)h->wl_list.ptr;
+    const bool any_ks = (o.tests & (NCB_TEST_KS | NCB_TEST_AUTO)) != 0;
+    NcbKsWork kw;
+    if (any_ks) {
+        int r = ks_work(h, 2 * P, kw);
+        if (r != NCB_OK) return r;
+    }
+
+    // ---- kernels -----------------------------------------------------------------------
+    int n;
+    n = ncb_launch_classify(a, wl, s);
+    if (n < 0) return fail(h, NCB_ERR_CUDA, "classify launch", cudaGetLastError());
+    h->launches += n;
+    if (time_it) CK(cudaEventRecord(h->ev[1], s));
+    n = ncb_launch_position_kernels(a, wl, h->sm_count, s);
+    if (n < 0) return fail(h, NCB_ERR_CUDA, "position kernel launch", cudaGetLastError());
+    h->launches += n;
+    if (time_it) CK(cudaEventRecord(h->ev[2], s));
+    if (any_ks) {
+        // rows NCB_PV_KS_INTENSITY, NCB_PV_KS_DWELL are the first two rows of pvalues: [2][P]
+        n = ncb_launch_ks_pvalues(2 * P, a.ks_n0, a.ks_n1, a.ks_h, a.pvalues, kw, h->sm_count, s);
+        if (n < 0) return fail(h, NCB_ERR_CUDA, "KS p-value launch", cudaGetLastError());
+        h->launches += n;
+    }
+    if (time_it) CK(cudaEventRecord(h->ev[3], s));
+    h->timed = time_it;
+
+    // ---- results -----------------------------------------------------------------------
+    if (out_host) {
+        CK(cudaMemcpyAsync(res->status, a.status, b_status, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(res->pvalues, a.pvalues, b_pv, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(res->stats, a.stats, b_st, cudaMemcpyDeviceToHost, s));
+        if (a.counts) CK(cudaMemcpyAsync(res->counts, a.counts, b_cnt, cudaMemcpyDeviceToHost, s));
+        if (a.diag_i64) CK(cudaMemcpyAsync(res->diag_i64, a.diag_i64, b_di, cudaMemcpyDeviceToHost, s));
+        if (a.diag_f64) CK(cudaMemcpyAsync(res->diag_f64, a.diag_f64, b_df, cudaMemcpyDeviceToHost, s));
+    }
+    return NCB_OK;
+}
+
+int ncb_wait(ncb_handle *h, void *stream) {
+    if (!h) return NCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return NCB_OK;
+}
+
+// copy helper of the unit entry points
+static int stage_in(ncb_handle *h, DevBuf &buf, const void *src, size_t bytes, int memory,
+                    cudaStream_t s, const void **dev) {
+    if (memory == NCB_MEM_DEVICE) { *dev = src; return NCB_OK; }
+    ENSURE(buf, bytes);
+    CK(cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, s));
+    *dev = buf.ptr;
+    return NCB_OK;
+}
+
+int ncb_ks_exact_pvalues(ncb_handle *h, int64_t n, const int32_t *n0, const int32_t *n1,
+                         const int64_t *hstat, double *p_out, int memory, void *stream) {
+    if (!h) return NCB_ERR_INVALID;
+    if (n < 0 || n > 0x7fffffffLL) return fail(h, NCB_ERR_INVALID, "ncb_ks_exact_pvalues: n out of range");
+    if (n == 0) return NCB_OK;
+    if (!n0 || !n1 || !hstat || !p_out) return fail(h, NCB_ERR_INVALID, "ncb_ks_exact_pvalues: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    const void *d0, *d1, *dh;
+    int r;
+    if ((r = stage_in(h, h->unit_a, n0, (size_t)n * 4, memory, s, &d0)) != NCB_OK) return r;
+    if ((r = stage_in(h, h->unit_b, n1, (size_t)n * 4, memory, s, &d1)) != NCB_OK) return r;
+    if ((r = stage_in(h, h->unit_c, hstat, (size_t)n * 8, memory, s, &dh)) != NCB_OK) return r;
+    double *dp = p_out;
+    if (memory == NCB_MEM_HOST) {
+        ENSURE(h->unit_d, (size_t)n * 8);
+        dp = (double *)h->unit_d.ptr;
+    }
+    NcbKsWork kw;
+    if ((r = ks_work(h, n, kw)) != NCB_OK) return r;
+    int k = ncb_launch_ks_pvalues(n, (const int32_t *)d0, (const int32_t *)d1, (const int64_t *)dh, dp,
+                                  kw, h->sm_count, s);
+    if (k < 0) return fail(h, NCB_ERR_CUDA, "KS p-value launch", cudaGetLastError());
+    h->launches += k;
+    if (memory == NCB_MEM_HOST) {
+        CK(cudaMemcpyAsync(p_out, dp, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return NCB_OK;
+}
+
+int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
+               int memory, void *stream) {
+    if (!h) return NCB_ERR_INVALID;
+    if (n < 0 || n > 0x7fffffffLL) return fail(h, NCB_ERR_INVALID, "ncb_bh_fdr: n out of range");
+    if (n == 0) return NCB_OK;
+    if (!pvalues || !qvalues) return fail(h, NCB_ERR_INVALID, "ncb_bh_fdr: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    size_t sb = ncb_bh_fdr_scratch_bytes(n);
+    ENSURE(h->fdr_scratch, sb);
+    const double *dp = pvalues;
+    double *dq = qvalues;
+    if (memory == NCB_MEM_HOST) {
+        ENSURE(h->fdr_p, (size_t)n * 8);
+        ENSURE(h->fdr_q, (size_t)n * 8);
+        CK(cudaMemcpyAsync(h->fdr_p.ptr, pvalues, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        dp = (const double *)h->fdr_p.ptr;
+        dq = (double *)h->fdr_q.ptr;
+    }
+    int k = ncb_launch_bh_fdr(n, dp, dq, scale, h->fdr_scratch.ptr, h->fdr_scratch.bytes, s);
+    if (k < 0) return fail(h, NCB_ERR_CUDA, "BH FDR launch", cudaGetLastError());
+    h->launches += k;
+    if (memory == NCB_MEM_HOST) {
+        CK(cudaMemcpyAsync(qvalues, dq, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return NCB_OK;
+}
+
+int64_t ncb_kernel_launches(const ncb_handle *h) { return h ? h->launches : 0; }
+
+int ncb_set_timing(ncb_handle *h, int enabled) {
+    if (!h) return NCB_ERR_INVALID;
+    h->timing = enabled ? 1 : 0;
+    return NCB_OK;
+}
+
+int ncb_last_timing(ncb_handle *h, float *ms_position, float *ms_ks, float *ms_total) {
+    if (!h) return NCB_ERR_INVALID;
+    if (!h->timed) return fail(h, NCB_ERR_INVALID, "ncb_last_timing: the last ncb_compare was not timed");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev[3]));
+    float a = 0, b = 0, c = 0;
+    CK(cudaEventElapsedTime(&a, h->ev[1], h->ev[2]));
+    CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
+    CK(cudaEventElapsedTime(&c, h->ev[0], h->ev[3]));
+    if (ms_position) *ms_position = a;
+    if (ms_ks) *ms_ks = b;
+    if (ms_total) *ms_total = c;
+    return NCB_OK;
+}
+
+}  // extern "C"

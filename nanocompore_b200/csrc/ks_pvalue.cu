@@ -1,0 +1,275 @@
+// Exact two-sided two-sample Kolmogorov-Smirnov p-values from the integer statistics
+// (n0, n1, h) the position kernel emits.
+//
+// Replaces scipy.stats._stats_py._attempt_exact_2kssamp (scipy/stats/_stats_py.py:7825-7870),
+// which nanocompore reaches through scipy.stats.mstats.ks_twosamp (comparisons.py:222,
+// 236-245):
+//   n0 == n1: _compute_prob_outside_square (7713-7748), an O(n) Horner product
+//   n0 != n1: _compute_outer_prob_inside_method (compiled in SciPy): the proportion of lattice
+//             paths (0,0)->(m,n) that leave the band |i/m - j/n| < h/lcm,
+//                 C(i,j) = (C(i-1,j)*i + C(i,j-1)*j) / (i+j),   C = 1 outside the band,
+//             C(0,j) = 0 inside the band; the answer is C(m,n).
+// Every cell is computed with the same three IEEE operations SciPy performs (no FMA
+// contraction, true division), so the result does not depend on how the cells are scheduled.
+//
+// The recurrence is sequential along a row, so problems are binned by kind and cost:
+//   SMALL  window <= 64 cells: one thread per problem, its window in shared memory
+//          (interleaved by thread: conflict free); a warp holds problems of one cost bucket
+//   EQUAL  one thread per problem
+//   LARGE / HUGE  one warp per problem: 32 rows advance together as a skewed wavefront
+//          (lane l is one column behind lane l-1 and takes the cell above by shuffle); the
+//          row above the 32-row chunk lives in shared memory.  Warps fetch problems from a
+//          counter, most expensive bucket first.
+#include "ncb_internal.h"
+#include "ncb_math.cuh"
+
+namespace ncb {
+
+__device__ __forceinline__ long long floordiv_ll(long long a, long long b) {  // b > 0
+    long long q = a / b;
+    if ((a % b) != 0 && a < 0) --q;
+    return q;
+}
+__device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   // a >= 0, b > 0
+    return (a + b - 1) / b;
+}
+
+struct KsProblem {
+    int m, n;            // m >= n
+    long long mg, ng, h;
+};
+
+__device__ __forceinline__ KsProblem make_problem(int n0, int n1, long long h) {
+    KsProblem q;
+    q.m = max(n0, n1);
+    q.n = min(n0, n1);
+    long long g = gcd_ll(n0, n1);
+    q.mg = q.m / g;
+    q.ng = q.n / g;
+    q.h = h;
+    return q;
+}
+
+__device__ __forceinline__ int cost_bucket(double cost) {
+    // two buckets per octave, bucket 0 = most expensive
+    int e;
+    double f = frexp(fmax(cost, 1.0), &e);   // cost = f * 2^e, f in [0.5, 1)
+    int b = 2 * e + (f >= 0.70710678118654752 ? 1 : 0);
+    b = NCB_KS_BUCKETS - 1 - b;
+    return b < 0 ? 0 : b;
+}
+
+__global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32_t *n1,
+                                   const int64_t *h, double *p_out, NcbKsWork w) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nprob;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        int a = n0[q], b = n1[q];
+        long long hh = h[q];
+        int bin = 255;
+        if (a <= 0 || b <= 0) {
+            p_out[q] = ncb_nan();
+        } else if (hh == 0) {
+            p_out[q] = 1.0;
+        } else if (a == b) {
+            bin = NCB_KS_KIND_EQUAL * NCB_KS_BUCKETS + cost_bucket((double)a + (double)hh);
+        } else {
+            KsProblem k = make_problem(a, b, hh);
+            long long maxj0 = min(ceildiv_ll(k.h, k.mg), (long long)k.n + 1);
+            long long lenA = min(2 * maxj0 + 2, (long long)k.n + 1);
+            double width = fmin(2.0 * (double)k.h / (double)k.mg + 1.0, (double)k.n + 1.0);
+            int kind = lenA <= NCB_KS_SMALL_WINDOW ? NCB_KS_KIND_SMALL
+                       : (k.n <= NCB_KS_LARGE_MAXN ? NCB_KS_KIND_LARGE : NCB_KS_KIND_HUGE);
+            bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
+        }
+        w.bin[q] = (uint8_t)bin;
+        if (bin != 255) atomicAdd(&w.hist[bin], 1);
+    }
+}
+
+// exclusive scan of the NCB_KS_NBINS counters (one block of NCB_KS_NBINS threads)
+__global__ void ks_scan_kernel(NcbKsWork w) {
+    __shared__ int s[NCB_KS_NBINS];
+    int t = threadIdx.x;
+    int v = w.hist[t];
+    s[t] = v;
+    __syncthreads();
+    for (int d = 1; d < NCB_KS_NBINS; d <<= 1) {
+        int y = t >= d ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += y;
+        __syncthreads();
+    }
+    int excl = s[t] - v;
+    w.hist[t] = excl;
+    w.cursor[t] = excl;
+    if (t == NCB_KS_NBINS - 1) w.hist[NCB_KS_NBINS] = s[t];
+    if (t < NCB_KS_KINDS) w.fetch[t] = 0;
+}
+
+__global__ void ks_scatter_kernel(int64_t nprob, NcbKsWork w) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nprob;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        int bin = w.bin[q];
+        if (bin != 255) {
+            int pos = atomicAdd(&w.cursor[bin], 1);
+            w.list[pos] = (int32_t)q;
+        }
+    }
+}
+
+// ---- thread per problem: unequal sizes, small window ------------------------------------
+#define KS_SMALL_THREADS 128
+__global__ void __launch_bounds__(KS_SMALL_THREADS)
+ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out,
+                NcbKsWork w) {
+    extern __shared__ double A_all[];   // [NCB_KS_SMALL_WINDOW][KS_SMALL_THREADS]
+    const int lo = w.hist[NCB_KS_KIND_SMALL * NCB_KS_BUCKETS];
+    const int hi = w.hist[(NCB_KS_KIND_SMALL + 1) * NCB_KS_BUCKETS];
+    const int idx = lo + blockIdx.x * KS_SMALL_THREADS + threadIdx.x;
+    if (idx >= hi) return;
+    const int q = w.list[idx];
+    const KsProblem k = make_problem(n0[q], n1[q], h[q]);
+    double *A = A_all + threadIdx.x;
+#define AT(j) A[(j) * KS_SMALL_THREADS]
+    const long long n = k.n, m = k.m, mg = k.mg, ng = k.ng, hh = k.h;
+    long long minj = 0, maxj = min(ceildiv_ll(hh, mg), n + 1);
+    long long curlen = maxj - minj;
+    for (int j = 0; j < NCB_KS_SMALL_WINDOW; ++j) AT(j) = (j < maxj) ? 0.0 : 1.0;
+    double result = -1.0;
+    for (long long i = 1; i <= m; ++i) {
+        const long long lastminj = minj, lastlen = curlen;
+        minj = max(floordiv_ll(ng * i - hh, mg) + 1, 0LL);
+        minj = min(minj, n);
+        maxj = min(ceildiv_ll(ng * i + hh, mg), n + 1);
+        if (maxj <= minj) { result = 1.0; break; }
+        double val = (minj == 0) ? 0.0 : 1.0;
+        const double di = (double)i;
+        const int shift = (int)(minj - lastminj);
+        const int len = (int)(maxj - minj);
+        for (int jj = 0; jj < len; ++jj) {
+            const long long j = jj + minj;
+            const int src = jj + shift;
+            const double up = (src < NCB_KS_SMALL_WINDOW) ? AT(src) : 1.0;
+            val = NCB_DDIV(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(val, (double)j)), (double)(i + j));
+            AT(jj) = val;
+        }
+        curlen = len;
+        for (long long jj = curlen; jj < lastlen; ++jj) AT(jj) = 1.0;
+    }
+    if (result < 0.0) result = AT(maxj - minj - 1);
+#undef AT
+    p_out[q] = clip01(result);
+}
+
+// ---- thread per problem: equal sizes -----------------------------------------------------
+__global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_out, NcbKsWork w) {
+    const int lo = w.hist[NCB_KS_KIND_EQUAL * NCB_KS_BUCKETS];
+    const int hi = w.hist[(NCB_KS_KIND_EQUAL + 1) * NCB_KS_BUCKETS];
+    const int idx = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hi) return;
+    const int q = w.list[idx];
+    p_out[q] = clip01(ks_prob_outside_square(n0[q], h[q]));
+}
+
+// ---- warp per problem: skewed wavefront over 32 rows --------------------------------------
+template <int WARPS, int ROWBUF>
+__global__ void __launch_bounds__(WARPS * 32)
+ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out,
+               NcbKsWork w, int kind) {
+    extern __shared__ double rows_all[];   // [WARPS][ROWBUF]
+    const int lane = threadIdx.x & 31;
+    double *prev = rows_all + (size_t)(threadIdx.x >> 5) * ROWBUF;
+    const int lo = w.hist[kind * NCB_KS_BUCKETS];
+    const int hi = w.hist[(kind + 1) * NCB_KS_BUCKETS];
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = lo + atomicAdd(&w.fetch[kind], 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= hi) break;
+        const int q = w.list[idx];
+        const KsProblem k = make_problem(n0[q], n1[q], h[q]);
+        const int n = k.n, m = k.m;
+        const long long mg = k.mg, ng = k.ng, hh = k.h;
+        const long long maxj0 = min(ceildiv_ll(hh, mg), (long long)n + 1);
+        for (int j = lane; j <= n; j += 32) prev[j] = (j < maxj0) ? 0.0 : 1.0;
+        __syncwarp();
+        for (int i0 = 1; i0 <= m; i0 += 32) {
+            const int rows = min(32, m - i0 + 1);
+            const int ilast = i0 + rows - 1;
+            long long jlo_l = max(floordiv_ll(ng * i0 - hh, mg) + 1, 0LL);
+            const int jlo = (int)min(jlo_l, (long long)n);
+            const int jhi = (int)min(ceildiv_ll(ng * ilast + hh, mg), (long long)n + 1);
+            const int i = i0 + lane;
+            const bool row_on = lane < rows;
+            const double di = (double)i;
+            const long long ngi = ng * i;
+            double left = 1.0, cur = 1.0;
+            const int nsteps = (jhi - jlo) + rows - 1;
+            for (int t = 0; t < nsteps; ++t) {
+                const int j = jlo + t - lane;
+                const double up_sh = __shfl_up_sync(0xffffffffu, cur, 1);
+                const bool act = row_on && j >= jlo && j < jhi;
+                if (act) {
+                    const double up = (lane == 0) ? prev[j] : up_sh;
+                    const long long v = ngi - mg * j;
+                    double val = 1.0;
+                    if ((v < 0 ? -v : v) < hh)
+                        val = NCB_DDIV(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, (double)j)),
+                                       (double)(i + j));
+                    cur = val;
+                    left = val;
+                    if (lane == rows - 1) prev[j] = val;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) p_out[q] = clip01(prev[n]);
+        __syncwarp();
+    }
+}
+
+}  // namespace ncb
+
+using namespace ncb;
+
+static const int KS_LARGE_WARPS = 8, KS_LARGE_BUF = NCB_KS_LARGE_MAXN + 1;
+static const int KS_HUGE_WARPS = 4, KS_HUGE_BUF = NCB_MAX_READS / 2 + 1;
+
+int ncb_configure_ks_kernels(void) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(ks_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS * (int)sizeof(double));
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             KS_LARGE_WARPS * KS_LARGE_BUF * (int)sizeof(double));
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             KS_HUGE_WARPS * KS_HUGE_BUF * (int)sizeof(double));
+    if (e != cudaSuccess) return -1;
+    return 0;
+}
+
+int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, const int64_t *h,
+                          double *p_out, const NcbKsWork &w, int sm_count, cudaStream_t s) {
+    if (nprob <= 0) return 0;
+    if (cudaMemsetAsync(w.hist, 0, (NCB_KS_NBINS + 1) * sizeof(int32_t), s) != cudaSuccess) return -1;
+    int blocks = (int)((nprob + 255) / 256);
+    if (blocks > sm_count * 8) blocks = sm_count * 8;
+    ks_classify_kernel<<<blocks, 256, 0, s>>>(nprob, n0, n1, h, p_out, w);
+    ks_scan_kernel<<<1, NCB_KS_NBINS, 0, s>>>(w);
+    ks_scatter_kernel<<<blocks, 256, 0, s>>>(nprob, w);
+    // the long problems first: their warps are busy while the short kernels fill the rest
+    ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF>
+        <<<sm_count, KS_HUGE_WARPS * 32, KS_HUGE_WARPS * KS_HUGE_BUF * sizeof(double), s>>>(
+            n0, n1, h, p_out, w, NCB_KS_KIND_HUGE);
+    ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF>
+        <<<sm_count * 3, KS_LARGE_WARPS * 32, KS_LARGE_WARPS * KS_LARGE_BUF * sizeof(double), s>>>(
+            n0, n1, h, p_out, w, NCB_KS_KIND_LARGE);
+    int tblocks = (int)((nprob + KS_SMALL_THREADS - 1) / KS_SMALL_THREADS);
+    ks_small_kernel<<<tblocks, KS_SMALL_THREADS,
+                      NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS * sizeof(double), s>>>(n0, n1, h, p_out, w);
+    ks_equal_kernel<<<tblocks, KS_SMALL_THREADS, 0, s>>>(n0, h, p_out, w);
+    return cudaGetLastError() == cudaSuccess ? 7 : -1;
+}

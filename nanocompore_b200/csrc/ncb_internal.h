@@ -1,0 +1,82 @@
+// Internal declarations shared by the libncb translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ncb.h"
+
+// Everything the device code needs to know about one ncb_compare call.
+struct NcbDeviceArgs {
+    // input
+    const float *signal;         // CSR [E][2] or dense [P][R][V]
+    const uint8_t *label;        // CSR [E] or dense [R]
+    const int64_t *pos_offsets;  // CSR [P+1] or nullptr (dense)
+    int64_t n_positions;
+    int32_t n_reads;             // dense R
+    int32_t n_vars;              // floats per entry (2 for CSR, V for dense)
+    // options
+    int32_t tests;
+    int32_t n_samples;
+    int32_t depleted_condition;
+    int32_t min_coverage;
+    int32_t dwell_is_raw;
+    int32_t cluster_counts;
+    int32_t em_max_iter;
+    double em_tol;
+    double reg_covar;
+    // output
+    int32_t *status;
+    double *pvalues;
+    float *stats;
+    uint32_t *counts;
+    int64_t *diag_i64;
+    double *diag_f64;
+    // scratch: exact-KS work items, one per (variable, position): index v * P + p
+    int32_t *ks_n0;
+    int32_t *ks_n1;
+    int64_t *ks_h;
+};
+
+// size classes of the position kernel, by entries per position
+//   class 0..2: one warp per position, 4 / 8 / 16 entries per lane
+//   class 3   : one 256-thread CTA per position, 8 entries per thread
+//   class 4   : one 1024-thread CTA per position, 10 entries per thread
+enum { NCB_NUM_CLASSES = 5 };
+static const int NCB_CLASS_CAP[NCB_NUM_CLASSES] = {128, 256, 512, 2048, NCB_MAX_READS};
+
+// worklists: class_count[c] positions in class_list[c * P ...]
+struct NcbWorklists {
+    int32_t *class_count;        // [NCB_NUM_CLASSES] device
+    int32_t *class_list;         // [NCB_NUM_CLASSES][P] device
+};
+
+// exact-KS p-value worklists: problems are binned by cost so that the threads of a warp
+// (thread-per-problem kernels) and consecutive warps (warp-per-problem kernel) do similar work
+#define NCB_KS_BUCKETS 64      /* cost buckets per kind (2 per octave of cost)           */
+enum { NCB_KS_KIND_SMALL = 0,  /* unequal sizes, DP window <= NCB_KS_SMALL_WINDOW: thread per problem */
+       NCB_KS_KIND_EQUAL = 1,  /* equal sizes: Horner product, thread per problem        */
+       NCB_KS_KIND_LARGE = 2,  /* unequal sizes, min(n0,n1) < 1024: warp wavefront       */
+       NCB_KS_KIND_HUGE = 3,   /* unequal sizes, min(n0,n1) >= 1024: warp wavefront, big buffer */
+       NCB_KS_KINDS = 4 };
+#define NCB_KS_SMALL_WINDOW 64
+#define NCB_KS_LARGE_MAXN 1023
+#define NCB_KS_NBINS (NCB_KS_KINDS * NCB_KS_BUCKETS)
+
+struct NcbKsWork {
+    int32_t *hist;      // [NCB_KS_NBINS + 1] counts -> exclusive offsets after the scan
+    int32_t *cursor;    // [NCB_KS_NBINS]
+    int32_t *list;      // [n_problems]
+    uint8_t *bin;       // [n_problems] bin of each problem, 255 = answered directly
+    int32_t *fetch;     // [NCB_KS_KINDS] dynamic work counters of the warp kernels
+};
+
+// launchers (each returns the number of kernels launched, or <0 on launch error)
+int ncb_launch_classify(const NcbDeviceArgs &a, const NcbWorklists &w, cudaStream_t s);
+int ncb_launch_position_kernels(const NcbDeviceArgs &a, const NcbWorklists &w, int sm_count,
+                                cudaStream_t s);
+int ncb_launch_ks_pvalues(int64_t n_problems, const int32_t *n0, const int32_t *n1,
+                          const int64_t *h, double *p_out, const NcbKsWork &w, int sm_count,
+                          cudaStream_t s);
+int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, void *scratch,
+                      size_t scratch_bytes, cudaStream_t s);
+size_t ncb_bh_fdr_scratch_bytes(int64_t n);
+int ncb_configure_kernels(void);  // cudaFuncSetAttribute for large dynamic shared memory

@@ -1,0 +1,325 @@
+"""
+Host side of the hot path: owns a libncb handle on one GPU, stages batches of positions
+(dense reference tensors or ragged CSR batches), launches the kernels on the current torch
+stream and returns the result columns.
+
+PyTorch is used for device memory, pinned host memory and streams only; every number in the
+results is produced by the CUDA kernels in nanocompore_b200/csrc (there is no CPU fallback:
+without a GPU or without libncb.so this module raises).
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from nanocompore_b200 import _lib as L
+
+TEST_BITS = {'KS': L.NCB_TEST_KS, 'MW': L.NCB_TEST_MW, 'TT': L.NCB_TEST_TT, 'GMM': L.NCB_TEST_GMM,
+             'LOGIT': L.NCB_TEST_LOGIT, 'AUTO': L.NCB_TEST_AUTO}
+COUNT_MODES = {None: L.NCB_COUNTS_NONE, 'none': L.NCB_COUNTS_NONE, 'hard': L.NCB_COUNTS_HARD,
+               'soft': L.NCB_COUNTS_SOFT}
+
+
+def tests_mask(methods, with_logit=False):
+    mask = 0
+    for m in methods:
+        key = m.upper()
+        if key not in TEST_BITS:
+            raise NotImplementedError(f"Test {m} is not implemented!")
+        mask |= TEST_BITS[key]
+    if with_logit:
+        mask |= L.NCB_TEST_LOGIT
+    return mask
+
+
+def make_labels(samples, conditions):
+    """label byte per read: bit 0 = condition (0 -> 0, anything else -> 1, as
+    comparisons.py:228-234 splits on ``conditions == 0``), bits 1..7 = sample id."""
+    samples = np.asarray(samples).astype(np.int64)
+    conditions = np.asarray(conditions).astype(np.int64)
+    if samples.size and (samples.min() < 0 or samples.max() >= L.NCB_MAX_SAMPLES):
+        raise ValueError(f"sample ids must be in [0, {L.NCB_MAX_SAMPLES})")
+    return ((samples << 1) | (conditions != 0)).astype(np.uint8)
+
+
+@dataclass
+class CsrBatch:
+    """Ragged batch: the valid reads of each position, position after position.
+
+    pos_offsets int64 [P+1]; signal float32 [E, 2] {intensity, dwell}; label uint8 [E].
+    Tensors are either all pinned-host or all on the device."""
+    pos_offsets: torch.Tensor
+    signal: torch.Tensor
+    label: torch.Tensor
+
+    @property
+    def n_positions(self):
+        return self.pos_offsets.numel() - 1
+
+    @property
+    def n_entries(self):
+        return self.signal.shape[0]
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.pos_offsets, self.signal, self.label))
+
+    def to(self, device, non_blocking=False):
+        return CsrBatch(self.pos_offsets.to(device, non_blocking=non_blocking),
+                        self.signal.to(device, non_blocking=non_blocking),
+                        self.label.to(device, non_blocking=non_blocking))
+
+    def pin(self):
+        return CsrBatch(self.pos_offsets.pin_memory(), self.signal.pin_memory(), self.label.pin_memory())
+
+
+def pack_csr(transcripts, pin=False):
+    """Packs dense reference tensors into one CSR batch.
+
+    ``transcripts``: iterable of (data (P,R,2) float32 with NaN, samples (R,), conditions (R,)).
+    A read is kept at a position when any of its two variables is a number.  Read order inside
+    a position is the read (column) order of the dense tensor.  Returns (CsrBatch,
+    pos_transcript int32 [P_total], pos_index int32 [P_total])."""
+    offs, sigs, labs, ptx, pidx = [np.zeros(1, dtype=np.int64)], [], [], [], []
+    total = 0
+    for ti, (data, samples, conditions) in enumerate(transcripts):
+        data = np.asarray(data, dtype=np.float32)
+        lab = make_labels(samples, conditions)
+        valid = ~np.isnan(data[:, :, :2]).all(2)            # (P, R)
+        counts = valid.sum(1).astype(np.int64)
+        sigs.append(data[:, :, :2][valid])                  # row-major: position, then read
+        labs.append(np.broadcast_to(lab[None, :], valid.shape)[valid])
+        offs.append(total + np.cumsum(counts))
+        total += int(counts.sum())
+        ptx.append(np.full(data.shape[0], ti, dtype=np.int32))
+        pidx.append(np.arange(data.shape[0], dtype=np.int32))
+    sig = np.concatenate(sigs) if sigs else np.zeros((0, 2), np.float32)
+    lab = np.concatenate(labs) if labs else np.zeros((0,), np.uint8)
+    batch = CsrBatch(torch.from_numpy(np.concatenate(offs)),
+                     torch.from_numpy(np.ascontiguousarray(sig.reshape(-1, 2))),
+                     torch.from_numpy(np.ascontiguousarray(lab)))
+    if pin:
+        batch = batch.pin()
+    return (batch,
+            np.concatenate(ptx) if ptx else np.zeros(0, np.int32),
+            np.concatenate(pidx) if pidx else np.zeros(0, np.int32))
+
+
+class Results:
+    """Result columns of one batch (struct of arrays, one slot per position)."""
+
+    def __init__(self, n_positions, n_samples, device, diagnostics=False, pinned=True):
+        P, S = n_positions, n_samples
+        self.n_positions, self.n_samples = P, S
+        on_dev = device is not None
+        kw = dict(device=device) if on_dev else dict(pin_memory=pinned)
+        self.memory = L.NCB_MEM_DEVICE if on_dev else L.NCB_MEM_HOST
+        self.status = torch.empty(P, dtype=torch.int32, **kw)
+        self.pvalues = torch.empty((L.NCB_PV_ROWS, P), dtype=torch.float64, **kw)
+        self.stats = torch.empty((L.NCB_ST_ROWS, P), dtype=torch.float32, **kw)
+        self.counts = torch.empty((max(S, 1), 2, P), dtype=torch.int32, **kw)
+        self.diag_i64 = torch.empty((L.NCB_DI_ROWS, P), dtype=torch.int64, **kw) if diagnostics else None
+        self.diag_f64 = torch.empty((L.NCB_DF_ROWS, P), dtype=torch.float64, **kw) if diagnostics else None
+
+    def struct(self):
+        r = L.NcbResults()
+        r.memory = self.memory
+        r.status = self.status.data_ptr()
+        r.pvalues = self.pvalues.data_ptr()
+        r.stats = self.stats.data_ptr()
+        r.counts = self.counts.data_ptr() if self.n_samples > 0 else None
+        r.diag_i64 = self.diag_i64.data_ptr() if self.diag_i64 is not None else None
+        r.diag_f64 = self.diag_f64.data_ptr() if self.diag_f64 is not None else None
+        return r
+
+    def nbytes(self):
+        ts = [self.status, self.pvalues, self.stats, self.counts, self.diag_i64, self.diag_f64]
+        return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+    # numpy views (host results, or device results copied back)
+    def numpy(self):
+        def get(t):
+            return None if t is None else t.cpu().numpy()
+        out = dict(status=get(self.status), pvalues=get(self.pvalues), stats=get(self.stats),
+                   counts=get(self.counts), diag_i64=get(self.diag_i64), diag_f64=get(self.diag_f64))
+        return out
+
+
+class Engine:
+    """One libncb handle on one CUDA device."""
+
+    def __init__(self, device=0, *, tests=('GMM', 'KS'), n_samples=4, depleted_condition=0,
+                 min_coverage=0, dwell_is_raw=False, cluster_counts='hard', with_logit=False,
+                 em_max_iter=100, em_tol=1e-3, reg_covar=1e-6):
+        if not torch.cuda.is_available():
+            raise RuntimeError("nanocompore_b200 needs a CUDA device: there is no CPU fallback")
+        self.lib = L.load()
+        if isinstance(device, str):
+            device = torch.device(device)
+        if isinstance(device, torch.device):
+            device = device.index if device.index is not None else torch.cuda.current_device()
+        self.device_index = int(device)
+        self.device = torch.device('cuda', self.device_index)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)   # make sure the primary context exists
+        self.opts = L.default_opts()
+        self._handle = C.c_void_p()
+        self.configure(tests=tests, n_samples=n_samples, depleted_condition=depleted_condition,
+                       min_coverage=min_coverage, dwell_is_raw=dwell_is_raw,
+                       cluster_counts=cluster_counts, with_logit=with_logit,
+                       em_max_iter=em_max_iter, em_tol=em_tol, reg_covar=reg_covar, _apply=False)
+        rc = self.lib.ncb_create(C.byref(self._handle), self.device_index, C.byref(self.opts))
+        if rc != L.NCB_OK:
+            self._handle = C.c_void_p()
+            raise L.NcbError(rc, "ncb_create failed (no usable GPU / library built for another arch)")
+
+    # ------------------------------------------------------------------ options
+    def configure(self, *, tests=None, n_samples=None, depleted_condition=None, min_coverage=None,
+                  dwell_is_raw=None, cluster_counts='__keep__', with_logit=None, em_max_iter=None,
+                  em_tol=None, reg_covar=None, _apply=True):
+        o = self.opts
+        if tests is not None:
+            logit = bool(with_logit) if with_logit is not None else bool(o.tests & L.NCB_TEST_LOGIT)
+            o.tests = tests if isinstance(tests, int) else tests_mask(tests, logit)
+        elif with_logit is not None:
+            o.tests = (o.tests & ~L.NCB_TEST_LOGIT) | (L.NCB_TEST_LOGIT if with_logit else 0)
+        if n_samples is not None:
+            o.n_samples = int(n_samples)
+        if depleted_condition is not None:
+            o.depleted_condition = int(depleted_condition)
+        if min_coverage is not None:
+            o.min_coverage = int(min_coverage)
+        if dwell_is_raw is not None:
+            o.dwell_is_raw = int(bool(dwell_is_raw))
+        if cluster_counts != '__keep__':
+            o.cluster_counts = COUNT_MODES[cluster_counts]
+        if em_max_iter is not None:
+            o.em_max_iter = int(em_max_iter)
+        if em_tol is not None:
+            o.em_tol = float(em_tol)
+        if reg_covar is not None:
+            o.reg_covar = float(reg_covar)
+        if _apply:
+            self._check(self.lib.ncb_set_opts(self._handle, C.byref(o)))
+
+    def _check(self, rc):
+        if rc == L.NCB_OK:
+            return
+        msg = self.lib.ncb_last_error(self._handle).decode(errors='replace')
+        if rc == L.NCB_ERR_NOMEM:
+            # keeps the caller's re-queue logic working (run.py:467-480)
+            raise torch.OutOfMemoryError(f"libncb: {msg}")
+        raise L.NcbError(rc, msg)
+
+    def close(self):
+        if self._handle:
+            self.lib.ncb_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ hot path
+    def _stream(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
+
+    def compare_csr(self, batch: CsrBatch, results: Results = None, *, diagnostics=False,
+                    stream=None, wait=True):
+        """Runs the hot path on a CSR batch (host-pinned or device tensors).  Results are
+        allocated where the batch lives unless ``results`` is given."""
+        on_dev = batch.signal.is_cuda
+        P = batch.n_positions
+        if results is None:
+            results = Results(P, self.opts.n_samples, self.device if on_dev else None, diagnostics)
+        b = L.NcbBatch()
+        b.layout = L.NCB_LAYOUT_CSR
+        b.memory = L.NCB_MEM_DEVICE if on_dev else L.NCB_MEM_HOST
+        b.n_positions = P
+        b.n_entries = batch.n_entries
+        assert batch.pos_offsets.dtype == torch.int64 and batch.signal.dtype == torch.float32
+        assert batch.label.dtype == torch.uint8
+        assert batch.signal.is_contiguous() and batch.label.is_contiguous()
+        b.pos_offsets = batch.pos_offsets.data_ptr()
+        b.signal = batch.signal.data_ptr()
+        b.label = batch.label.data_ptr()
+        r = results.struct()
+        s = self._stream(stream)
+        self._check(self.lib.ncb_compare(self._handle, C.byref(b), C.byref(r), s))
+        if wait:
+            self._check(self.lib.ncb_wait(self._handle, s))
+        return results
+
+    def compare_dense(self, data: torch.Tensor, labels: torch.Tensor, results: Results = None, *,
+                      diagnostics=False, stream=None, wait=True):
+        """Runs the hot path on the reference's dense tensor ``data`` (P, R, V) float32 with
+        NaN for missing reads, ``labels`` uint8 (R,) from ``make_labels``."""
+        assert data.dtype == torch.float32 and data.dim() == 3 and data.is_contiguous()
+        assert labels.dtype == torch.uint8 and labels.is_contiguous()
+        on_dev = data.is_cuda
+        assert labels.is_cuda == on_dev
+        P, R, V = data.shape
+        if results is None:
+            results = Results(P, self.opts.n_samples, self.device if on_dev else None, diagnostics,
+                              pinned=False)
+        b = L.NcbBatch()
+        b.layout = L.NCB_LAYOUT_DENSE
+        b.memory = L.NCB_MEM_DEVICE if on_dev else L.NCB_MEM_HOST
+        b.n_positions = P
+        b.n_entries = P * R
+        b.pos_offsets = None
+        b.signal = data.data_ptr()
+        b.label = labels.data_ptr()
+        b.n_reads = R
+        b.n_vars = V
+        r = results.struct()
+        s = self._stream(stream)
+        self._check(self.lib.ncb_compare(self._handle, C.byref(b), C.byref(r), s))
+        if wait:
+            self._check(self.lib.ncb_wait(self._handle, s))
+        return results
+
+    def wait(self, stream=None):
+        self._check(self.lib.ncb_wait(self._handle, self._stream(stream)))
+
+    # ------------------------------------------------------------------ unit entry points
+    def ks_exact_pvalues(self, n0, n1, h):
+        n0 = np.ascontiguousarray(n0, dtype=np.int32)
+        n1 = np.ascontiguousarray(n1, dtype=np.int32)
+        h = np.ascontiguousarray(h, dtype=np.int64)
+        out = np.empty(n0.size, dtype=np.float64)
+        self._check(self.lib.ncb_ks_exact_pvalues(
+            self._handle, n0.size, n0.ctypes.data, n1.ctypes.data, h.ctypes.data, out.ctypes.data,
+            L.NCB_MEM_HOST, self._stream()))
+        return out
+
+    def bh_fdr(self, pvalues, scale=1.0):
+        """Benjamini-Hochberg q-values, NaNs skipped (postprocessing.py:255-285).  Accepts a
+        numpy array (host) or a CUDA float64 tensor (stays on the device)."""
+        if isinstance(pvalues, torch.Tensor) and pvalues.is_cuda:
+            p = pvalues.contiguous().to(torch.float64)
+            q = torch.empty_like(p)
+            self._check(self.lib.ncb_bh_fdr(self._handle, p.numel(), p.data_ptr(), q.data_ptr(),
+                                            float(scale), L.NCB_MEM_DEVICE, self._stream()))
+            return q
+        p = np.ascontiguousarray(pvalues, dtype=np.float64)
+        q = np.empty_like(p)
+        self._check(self.lib.ncb_bh_fdr(self._handle, p.size, p.ctypes.data, q.ctypes.data,
+                                        float(scale), L.NCB_MEM_HOST, self._stream()))
+        return q
+
+    # ------------------------------------------------------------------ introspection
+    def kernel_launches(self):
+        return int(self.lib.ncb_kernel_launches(self._handle))
+
+    def set_timing(self, enabled=True):
+        self._check(self.lib.ncb_set_timing(self._handle, int(enabled)))
+
+    def last_timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self._check(self.lib.ncb_last_timing(self._handle, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(ms_position=a.value, ms_ks=b.value, ms_total=c.value)
