@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""
+bench.py -- tested positions/sec of the per-position comparison hot path (GMM + KS).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path
+
+Workload = BASELINE.json configs[2] ("config 3"): synthetic transcripts of 2,000 positions x
+2x2 replicates x 100 reads per condition, comparison_methods [GMM, KS], the coverage filter
+(min_coverage 30) and log10(dwell) inside the timed path.  One step = one batch of
+``--tx-per-step`` transcripts (default 50 -> 100,000 positions, ~180 MB of reads: larger than
+the 126 MB L2, and every step reads a different batch).  K = 20 steps is the whole config.
+
+Printed JSON (one line, rank 0):
+  value     positions/s with the CSR batches already resident in HBM (device timed, CUDA events)
+  e2e       positions/s through the public API with pinned HOST batches: H2D copy of the reads,
+            kernels and D2H copy of the result columns inside the timed region (two engines on
+            two streams so that the copies of one batch overlap the kernels of the other)
+  roofline  HBM roofline of the dominant kernel (position kernel), live CUDA-event timing
+  cpu_baseline  the oracle port (oracle/comparator.py: numpy + SciPy per position, as the
+            reference does) on one host core, on a bounded sample of the same workload
+
+``--impl reference`` times that same CPU port on ALL host cores (one process per core over
+transcripts, as the reference's ``devices: {cpu: C}`` does, run.py:104-131).  The reference is
+pure Python and its GMM lives in the absent third-party package gmm-gpu, so the CPU arm is the
+port: "reference algorithm, restated gmm_gpu".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIG_INDEX = 3
+N_POSITIONS = 2000
+READS_PER_COND = 100
+METHODS = ['GMM', 'KS']
+MIN_COVERAGE = 30
+METRIC = "tested positions/sec (GMM+KS)"
+UNIT = "positions/s"
+SAMPLE_IDS = {'kd1': 0, 'kd2': 1, 'wt1': 2, 'wt2': 3}
+
+
+def workload_name(tx_per_step):
+    return (f"config3: transcripts of {N_POSITIONS} positions x 2x2 replicates x {READS_PER_COND} "
+            f"reads/condition, [GMM, KS], min_coverage {MIN_COVERAGE}; step = {tx_per_step} transcripts")
+
+
+def make_batch_transcripts(seed, n_tx):
+    from nanocompore_b200.synthetic import make_transcript
+    rng = np.random.default_rng(seed)
+    return [make_transcript(rng, N_POSITIONS, READS_PER_COND, name=f'tx{seed}_{i}') for i in range(n_tx)]
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the oracle port
+# ----------------------------------------------------------------------------------------
+
+def cpu_compare_transcript(tx):
+    """One transcript through the CPU port: prep (run.py:511-601) + compare_transcript."""
+    from oracle import prep as oprep
+    from oracle.comparator import OracleComparator, OracleConfig
+    data, samples, conditions, positions = oprep.prepare_data(tx.data, tx.samples, tx.conditions)
+    data, positions = oprep.filter_low_cov_positions(data, positions, conditions, MIN_COVERAGE)
+    cmp_ = OracleComparator(OracleConfig(comparison_methods=METHODS, sample_ids=SAMPLE_IDS))
+    df = cmp_.compare_transcript(tx.name, data, samples, conditions, positions)
+    return 0 if df is None else len(df)
+
+
+def _cpu_worker(args):
+    seed, n_positions = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    from nanocompore_b200.synthetic import make_transcript
+    rng = np.random.default_rng(seed)
+    tx = make_transcript(rng, n_positions, READS_PER_COND, name=f'cpu{seed}')
+    t0 = time.perf_counter()
+    rows = cpu_compare_transcript(tx)
+    return rows, time.perf_counter() - t0
+
+
+def cpu_baseline_single_core(budget_s=20.0, n_positions=500):
+    """Bounded sample on one core: slices of config-3 transcripts until ~budget_s."""
+    rows, spent, n = 0, 0.0, 0
+    while spent < budget_s and n < 64:
+        r, dt = _cpu_worker((977 + n, n_positions))
+        rows += r
+        spent += dt
+        n += 1
+    return dict(value=rows / spent, unit=UNIT, cores=1, kind="port",
+                sample=f"{n} slices of {n_positions} positions x {2 * READS_PER_COND} reads "
+                       f"({rows} tested positions, {spent:.1f} s)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_positions = args.ref_positions
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores) as pool:
+        def step(i):
+            t0 = time.perf_counter()
+            out = pool.map(_cpu_worker, [(100000 + i * cores + c, n_positions) for c in range(cores)])
+            return sum(r for r, _ in out), time.perf_counter() - t0
+        for i in range(args.warmup):
+            step(i)
+        rows, total = 0, 0.0
+        for i in range(args.steps):
+            r, dt = step(args.warmup + i)
+            rows += r
+            total += dt
+    value = rows / total
+    sample = (f"{args.steps} steps x {cores} slices of {n_positions} positions x "
+              f"{2 * READS_PER_COND} reads, one process per core")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.tx_per_step), "cpu_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from nanocompore_b200 import _lib as L
+    from nanocompore_b200.engine import Engine, Results, pack_csr
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+
+    K, W, T = args.steps, args.warmup, args.tx_per_step
+    n_batches = K + W
+    opts = dict(tests=METHODS, n_samples=4, depleted_condition=0, min_coverage=MIN_COVERAGE,
+                dwell_is_raw=True, cluster_counts='hard')
+    engines = [Engine(local_rank, **opts) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+    # ---- synthetic batches: pinned host copies (e2e) and device copies (value) ------------
+    host_batches, dev_batches = [], []
+    t_gen = time.perf_counter()
+    for b in range(n_batches):
+        txs = make_batch_transcripts(20251019 + CONFIG_INDEX + 1000 * rank + b, T)
+        batch, _, _ = pack_csr([(t.data, t.samples, t.conditions) for t in txs], pin=True)
+        host_batches.append(batch)
+        dev_batches.append(batch.to(dev))
+    t_gen = time.perf_counter() - t_gen
+    P = host_batches[0].n_positions
+    h2d_bytes = int(np.mean([b.nbytes() for b in host_batches[W:]]))
+    entries = int(np.mean([b.n_entries for b in host_batches[W:]]))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- value: device-resident inputs ------------------------------------------------------
+    eng = engines[0]
+    res_dev = Results(P, 4, dev)
+    tested = torch.zeros((), dtype=torch.int64, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def value_step(b):
+        eng.compare_csr(dev_batches[b], res_dev, wait=False)
+        return ((res_dev.status & L.NCB_POS_DROP_MASK) == 0).sum()
+
+    for b in range(W):
+        tested += value_step(b)
+    tested.zero_()
+    eng.set_timing(True)
+    launches0 = eng.kernel_launches()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for b in range(W, n_batches):
+        tested += value_step(b)
+    ev1.record()
+    barrier()
+    ms_value = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.kernel_launches() - launches0
+    totals = eng.timing_totals()
+    eng.set_timing(False)
+    tested_positions = int(tested.item())
+    total_tested = sum_over_ranks(float(tested_positions))
+    value = total_tested / (ms_value / 1000.0)
+
+    # ---- e2e: pinned host batches through the public API, copies inside the timed region ---
+    res_host = [Results(P, 4, None) for _ in range(2)]
+    for b in range(W):
+        engines[b % 2].compare_csr(host_batches[b], res_host[b % 2], stream=streams[b % 2], wait=False)
+    barrier()
+    t0 = time.perf_counter()
+    tested_host = 0
+    pending = [None, None]
+    for i, b in enumerate(range(W, n_batches)):
+        s = i % 2
+        if pending[s] is not None:
+            engines[s].wait(streams[s])
+            tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
+        engines[s].compare_csr(host_batches[b], res_host[s], stream=streams[s], wait=False)
+        pending[s] = b
+    for s in range(2):
+        if pending[s] is not None:
+            engines[s].wait(streams[s])
+            tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
+    torch.cuda.synchronize(dev)
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+    clocks = sampler.stop()
+    total_tested_host = sum_over_ranks(float(tested_host))
+    e2e_value = total_tested_host / (ms_e2e / 1000.0)
+    d2h_bytes = res_host[0].nbytes()
+    total_launches = int(sum_over_ranks(float(launches)))
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (position kernel), HBM bound --------------------
+    # algorithmic bytes per launch: every read once (8 B signal + 1 B label), the CSR offsets,
+    # and the result columns written once per position
+    out_bytes_per_pos = 4 + 8 * L.NCB_PV_ROWS + 4 * L.NCB_ST_ROWS + 4 * 2 * 4 + (4 + 4 + 8) * 2
+    alg_bytes = entries * 9 + P * (8 + out_bytes_per_pos)
+    ms_pos = totals['ms_position'] / max(totals['batches'], 1)
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms_pos / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "position_kernel_warp<256,8>", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "ms_per_launch": ms_pos,
+                "ms_ks_pvalue_kernels": totals['ms_ks'] / max(totals['batches'], 1),
+                "ms_classify": totals['ms_classify'] / max(totals['batches'], 1),
+                "note": "the kernel is fp64-pipe bound (EM in fp64), not HBM bound; see DESIGN.md"}
+    ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(ncu_traffic):
+        try:
+            with open(ncu_traffic) as f:
+                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = cpu_baseline_single_core(args.cpu_budget) if not args.no_cpu_baseline else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(T), "positions_per_step": P,
+                   "tested_positions_per_step": tested_positions / K,
+                   "reads_per_step": entries, "l2": "inputs larger than L2, distinct batch per step",
+                   "parallelism": f"transcript sharding x{world}, no data-path collective"},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / K},
+        "gpu_launches": total_launches,
+        "clocks": clocks,
+        "setup_s": {"generate_and_pack": t_gen},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--tx-per-step', type=int, default=50)
+    ap.add_argument('--cpu-budget', type=float, default=20.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-positions', type=int, default=250,
+                    help="positions per slice of the reference arm (one slice per core per step)")
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

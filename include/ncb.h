@@ -222,6 +222,11 @@ int64_t ncb_kernel_launches(const ncb_handle *h);
  * whose batch was timed (set NCB_TIMING=1 in the environment or call ncb_set_timing). */
 int ncb_set_timing(ncb_handle *h, int enabled);
 int ncb_last_timing(ncb_handle *h, float *ms_position_kernels, float *ms_ks_kernels, float *ms_total);
+/* Sums over every ncb_compare since the last ncb_set_timing(h, 1): number of batches and the
+ * device milliseconds (CUDA events on the caller's stream) of the staging copy + classification,
+ * of the position kernels and of the KS p-value kernels.  Blocks until those batches are done. */
+int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_position,
+                      double *ms_ks);
 
 #ifdef __cplusplus
 }

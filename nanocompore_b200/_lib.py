@@ -43,7 +43,7 @@ NCB_DF_ROWS = 17
 
 EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
-           'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing']
+           'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals']
 
 
 class NcbOpts(C.Structure):
@@ -111,6 +111,9 @@ def load():
     lib.ncb_set_timing.restype = C.c_int
     lib.ncb_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.ncb_last_timing.restype = C.c_int
+    lib.ncb_timing_totals.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double)]
+    lib.ncb_timing_totals.restype = C.c_int
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
     _lib = lib

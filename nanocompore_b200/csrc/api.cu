@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <vector>
 #include "ncb_internal.h"
 
 int ncb_configure_ks_kernels(void);
@@ -19,8 +20,9 @@ struct ncb_handle {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // events of the last timed batch
     bool timed = false;
+    std::vector<cudaEvent_t> ev_log;   // 4 events per timed batch since ncb_set_timing(h, 1)
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
@@ -145,7 +147,6 @@ int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
         delete h;
         return NCB_ERR_CUDA;
     }
-    for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
     const char *t = getenv("NCB_TIMING");
     h->timing = (t && t[0] == '1') ? 1 : 0;
     *out = h;
@@ -169,8 +170,7 @@ void ncb_destroy(ncb_handle *h) {
                      &h->kw_bin, &h->kw_fetch, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d};
     for (DevBuf *b : all) release(*b);
-    for (int i = 0; i < 4; ++i)
-        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ev_log) cudaEventDestroy(e);
     delete h;
 }
 
@@ -238,7 +238,15 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     a.reg_covar = o.reg_covar;
 
     const bool time_it = h->timing != 0;
-    if (time_it) CK(cudaEventRecord(h->ev[0], s));
+    if (time_it) {
+        for (int i = 0; i < 4; ++i) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->ev_log.push_back(e);
+            h->ev[i] = e;
+        }
+        CK(cudaEventRecord(h->ev[0], s));
+    }
 
     // ---- inputs ------------------------------------------------------------------------
     if (b->memory == NCB_MEM_HOST) {
@@ -422,6 +430,35 @@ int64_t ncb_kernel_launches(const ncb_handle *h) { return h ? h->launches : 0; }
 int ncb_set_timing(ncb_handle *h, int enabled) {
     if (!h) return NCB_ERR_INVALID;
     h->timing = enabled ? 1 : 0;
+    if (enabled) {   // start a new log
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        for (cudaEvent_t e : h->ev_log) cudaEventDestroy(e);
+        h->ev_log.clear();
+        h->timed = false;
+    }
+    return NCB_OK;
+}
+
+int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_position,
+                      double *ms_ks) {
+    if (!h) return NCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    double a = 0, b = 0, c = 0;
+    const size_t nb = h->ev_log.size() / 4;
+    for (size_t i = 0; i < nb; ++i) {
+        cudaEvent_t *e = &h->ev_log[4 * i];
+        CK(cudaEventSynchronize(e[3]));
+        float x = 0, y = 0, z = 0;
+        CK(cudaEventElapsedTime(&x, e[0], e[1]));
+        CK(cudaEventElapsedTime(&y, e[1], e[2]));
+        CK(cudaEventElapsedTime(&z, e[2], e[3]));
+        a += x; b += y; c += z;
+    }
+    if (n_batches) *n_batches = (int64_t)nb;
+    if (ms_classify) *ms_classify = a;
+    if (ms_position) *ms_position = b;
+    if (ms_ks) *ms_ks = c;
     return NCB_OK;
 }
 

@@ -323,3 +323,9 @@ class Engine:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         self._check(self.lib.ncb_last_timing(self._handle, C.byref(a), C.byref(b), C.byref(c)))
         return dict(ms_position=a.value, ms_ks=b.value, ms_total=c.value)
+
+    def timing_totals(self):
+        """Sums of the CUDA-event timings of every batch since ``set_timing(True)``."""
+        n, a, b, c = C.c_int64(), C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.ncb_timing_totals(self._handle, C.byref(n), C.byref(a), C.byref(b), C.byref(c)))
+        return dict(batches=n.value, ms_classify=a.value, ms_position=b.value, ms_ks=c.value)

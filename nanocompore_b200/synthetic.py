@@ -41,25 +41,26 @@ def make_transcript(rng, n_positions, reads_per_cond, *, quantised=False,
     conditions = (samples >= n_replicates).astype(np.int16)
     assert samples.size == R and S == 2 * n_replicates
 
-    mu = rng.uniform(60.0, 130.0, size=P)
-    sigma = rng.uniform(2.0, 6.0, size=P)
-    inten = rng.standard_normal((P, R)) * sigma[:, None] + mu[:, None]
-    dwell = np.exp(rng.standard_normal((P, R)) * 0.5 + np.log(0.01))
+    f32 = np.float32
+    mu = rng.uniform(60.0, 130.0, size=P).astype(f32)
+    sigma = rng.uniform(2.0, 6.0, size=P).astype(f32)
+    inten = rng.standard_normal((P, R), dtype=f32) * sigma[:, None] + mu[:, None]
+    dwell = np.exp(rng.standard_normal((P, R), dtype=f32) * f32(0.5) + f32(np.log(0.01)))
 
     modified = rng.random(P) < mod_fraction
-    frac = rng.uniform(0.3, 0.9, size=P)
-    hit = (rng.random((P, R)) < frac[:, None]) & modified[:, None] & (conditions[None, :] == 1)
-    inten = np.where(hit, inten + 3.0 * sigma[:, None], inten)
-    dwell = np.where(hit, dwell * 1.6, dwell)
+    frac = rng.uniform(0.3, 0.9, size=P).astype(f32)
+    hit = (rng.random((P, R), dtype=f32) < frac[:, None]) & modified[:, None] & (conditions[None, :] == 1)
+    inten = np.where(hit, inten + f32(3.0) * sigma[:, None], inten)
+    dwell = np.where(hit, dwell * f32(1.6), dwell)
 
     if quantised:
         # mimics Uncalled4 int16 current levels / integer sample counts: true ties
-        inten = np.round(inten * 64.0) / 64.0
-        dwell = np.maximum(np.round(dwell * 4000.0), 1.0) / 4000.0
+        inten = np.round(inten * f32(64.0)) / f32(64.0)
+        dwell = np.maximum(np.round(dwell * f32(4000.0)), f32(1.0)) / f32(4000.0)
 
     start = (rng.uniform(0.0, span_start_max, size=R) * P).astype(np.int64)
     covered = np.arange(P)[:, None] >= start[None, :]
-    covered &= rng.random((P, R)) >= gap_rate
+    covered &= rng.random((P, R), dtype=f32) >= gap_rate
 
     data = np.empty((P, R, 2), dtype=np.float32)
     data[:, :, 0] = np.where(covered, inten, np.nan)
