@@ -168,7 +168,7 @@ __global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_o
     const int idx = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= hi) return;
     const int q = w.list[idx];
-    p_out[q] = clip01(ks_prob_outside_square(n0[q], h[q]));
+    p_out[q] = ks_equal_p(n0[q], h[q]);
 }
 
 // ---- warp per problem: skewed wavefront over 32 rows --------------------------------------

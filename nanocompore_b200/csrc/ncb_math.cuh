@@ -216,4 +216,26 @@ NCB_HD inline double ks_prob_outside_square(long long n, long long h) {
     return 2.0 * P;
 }
 
+// Equal sample sizes: the Horner product, and SciPy's behaviour when its rounding lands
+// outside [0, 1] (only ever just above 1, when the true probability is 1 - O(1e-16)):
+// _attempt_exact_2kssamp reports failure and ks_2samp falls back to the one-sample Kolmogorov
+// distribution kstwo.sf(d = h/n, N = round-half-even(n/2)) (_stats_py.py:8156-8171).  In that
+// regime only the first two branches of kolmogn matter:
+//     d <= 1/(2N): 1          1/(2N) < d <= 1/N: 1 - N! (2d - 1/N)^N        else: 1
+// (the third branch drops a term below 4e-13, checked against SciPy for every n that can
+// reach it; tests/test_math_host.py).
+NCB_HD inline double ks_equal_p(long long n, long long h) {
+    double p = ks_prob_outside_square(n, h);
+    if (p >= 0.0 && p <= 1.0) return p;
+    const double d = (double)h / (double)n;
+    const double N = rint(0.5 * (double)n);
+    if (N < 1.0 || d <= 1.0 / (2.0 * N)) return 1.0;
+    if (d <= 1.0 / N) {
+        const double base = 2.0 * d - 1.0 / N;
+        if (!(base > 0.0)) return 1.0;
+        return clip01(1.0 - exp(lgamma(N + 1.0) + N * log(base)));
+    }
+    return 1.0;
+}
+
 }  // namespace ncb

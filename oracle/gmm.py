@@ -25,10 +25,15 @@ and defines the fit as scikit-learn ``GaussianMixture(covariance_type='full')`` 
 * BIC     -2 N L + n_params ln N,  n_params = K D + K D (D+1)/2 + K - 1
 * K = 1   closed form (sample mean, population covariance + reg_covar*I)
 * K = 2   initialisation is deterministic (no RNG, so ``random_seed`` is accepted and
-          ignored): c0 = valid read closest to the mean of the valid reads, c1 = valid
-          read farthest from c0 (ties -> lowest read index); every read is hard-assigned
-          to the nearer of c0/c1 (tie -> component 0); one M-step on those 0/1
-          responsibilities gives the starting parameters.
+          ignored) and k-means based, like scikit-learn's default ``init_params='kmeans'``:
+          centre 0 = the valid read farthest from the mean of the valid reads, centre 1 = the
+          valid read farthest from centre 0 (ties -> lowest read index); then Lloyd iterations
+          (assign every read to the nearer centre, tie -> cluster 0; centres = cluster means; an
+          emptied cluster keeps its centre) until no assignment changes, at most 20; one M-step
+          on the final 0/1 responsibilities gives the starting parameters.
+          (A first version of this definition seeded the second component on the single
+          farthest read; that isolates an extreme read in a component of its own and failed the
+          reference's own tests tests/test_comparisons.py:464-504.)
 * fewer than 2 valid reads: the fit is undefined -> BIC and posteriors are NaN.
 
 Test infrastructure only (see oracle/__init__.py).
@@ -41,7 +46,8 @@ LOG_2PI = float(np.log(2 * np.pi))
 
 class GMM:
     def __init__(self, n_components, device='cpu', random_seed=None, dtype=None,
-                 max_iter=100, tol=1e-3, reg_covar=1e-6, work_dtype=np.float64):
+                 max_iter=100, tol=1e-3, reg_covar=1e-6, work_dtype=np.float64,
+                 kmeans_max_iter=20):
         if n_components not in (1, 2):
             raise NotImplementedError("only K=1 and K=2 are used by nanocompore")
         self.K = n_components
@@ -49,10 +55,22 @@ class GMM:
         self.tol = tol
         self.reg = reg_covar
         self.wd = work_dtype
+        self.kmeans_max_iter = kmeans_max_iter
         self.n_iter = None
         self._torch_out = False
 
     # ------------------------------------------------------------------ utils
+    @staticmethod
+    def _dist2(Xz, c):
+        """squared distance of every read to a centre per position: dx*dx + dy*dy (+ ...),
+        each product and sum rounded once (no fused multiply-add)."""
+        d = Xz - c[:, None, :]
+        sq = d * d
+        out = sq[:, :, 0]
+        for k in range(1, sq.shape[2]):
+            out = out + sq[:, :, k]
+        return out
+
     def _prep(self, X):
         try:
             import torch
@@ -112,18 +130,39 @@ class GMM:
                 w, mu, cov = self._moments(Xz, R)
                 self.n_iter = np.zeros(B, dtype=np.int32)
             else:
-                # deterministic farthest-point initialisation
+                # deterministic 2-means initialisation (see the module docstring)
+                ar = np.arange(B)
                 mean = (Xz * vf[:, :, None]).sum(1) / np.maximum(n, 1)[:, None]
-                d0 = ((Xz - mean[:, None, :]) ** 2).sum(2)
-                d0 = np.where(valid, d0, np.inf)
-                c0 = d0.argmin(1)
-                p0 = Xz[np.arange(B), c0]
-                dc0 = ((Xz - p0[:, None, :]) ** 2).sum(2)
-                c1 = np.where(valid, dc0, -np.inf).argmax(1)
-                p1 = Xz[np.arange(B), c1]
-                dc1 = ((Xz - p1[:, None, :]) ** 2).sum(2)
-                a0 = (dc0 <= dc1)
-                R = np.stack([a0, ~a0], axis=2).astype(self.wd) * vf[:, :, None]
+                dm = self._dist2(Xz, mean)
+                c0 = np.where(valid, dm, -np.inf).argmax(1)         # farthest from the mean
+                p0 = Xz[ar, c0]
+                c1 = np.where(valid, self._dist2(Xz, p0), -np.inf).argmax(1)   # farthest from it
+                p1 = Xz[ar, c1]
+                assign = None
+                self.n_kmeans = np.zeros(B, dtype=np.int32)
+                live = self._ok.copy()
+                for it in range(1, self.kmeans_max_iter + 1):
+                    a0 = self._dist2(Xz, p0) <= self._dist2(Xz, p1)          # tie -> cluster 0
+                    if assign is not None:
+                        changed = ((a0 != assign) & valid).any(1)
+                        live &= changed
+                    assign = np.where(live[:, None], a0, assign) if it > 1 else a0
+                    if not live.any():
+                        break
+                    self.n_kmeans[live] = it
+                    w0 = (assign & valid).astype(self.wd)
+                    w1 = (~assign & valid).astype(self.wd)
+                    n0 = w0.sum(1)
+                    n1 = w1.sum(1)
+                    with np.errstate(invalid='ignore', divide='ignore'):
+                        q0 = (Xz * w0[:, :, None]).sum(1) / n0[:, None]
+                        q1 = (Xz * w1[:, :, None]).sum(1) / n1[:, None]
+                    # an emptied cluster keeps its centre
+                    q0 = np.where((n0 > 0)[:, None], q0, p0)
+                    q1 = np.where((n1 > 0)[:, None], q1, p1)
+                    p0 = np.where(live[:, None], q0, p0)
+                    p1 = np.where(live[:, None], q1, p1)
+                R = np.stack([assign, ~assign], axis=2).astype(self.wd) * vf[:, :, None]
                 w, mu, cov = self._moments(Xz, R)
 
                 active = self._ok.copy()

@@ -14,5 +14,6 @@ double hc_mwu_exact_p(long long umin, long long n0, long long n1) {
 double hc_chi2_2x2_p(double a, double b, double c, double d) { return ncb::chi2_2x2_p(a, b, c, d); }
 void hc_logit_wald(double a, double b, double c, double d, double *coef, double *p) { ncb::logit_wald(a, b, c, d, coef, p); }
 double hc_ks_prob_outside_square(long long n, long long h) { return ncb::ks_prob_outside_square(n, h); }
+double hc_ks_equal_p(long long n, long long h) { return ncb::ks_equal_p(n, h); }
 double hc_normal_two_sided(double z) { return ncb::normal_two_sided(z); }
 }

@@ -1,0 +1,150 @@
+"""
+The scalar fp64 routines the kernels call once per position (nanocompore_b200/csrc/ncb_math.cuh),
+compiled for the host by __graft_entry__.build() and checked against SciPy on the CPU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy import stats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, 'build', 'host_check.so')
+
+
+@pytest.fixture(scope='module')
+def hc():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    src = os.path.join(ROOT, 'tests', 'csrc', 'host_check.cpp')
+    hdr = os.path.join(ROOT, 'nanocompore_b200', 'csrc', 'ncb_math.cuh')
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(['g++', '-O2', '-shared', '-fPIC', '-ffp-contract=off',
+                        '-I', os.path.join(ROOT, 'nanocompore_b200', 'csrc'), src, '-o', SO], check=True)
+    lib = C.CDLL(SO)
+    d, ll = C.c_double, C.c_longlong
+    lib.hc_student_t_two_sided.restype = d; lib.hc_student_t_two_sided.argtypes = [d, d]
+    lib.hc_welch_p.restype = d; lib.hc_welch_p.argtypes = [d] * 6
+    lib.hc_mwu_asymptotic_p.restype = d; lib.hc_mwu_asymptotic_p.argtypes = [ll] * 4
+    lib.hc_mwu_exact_p.restype = d; lib.hc_mwu_exact_p.argtypes = [ll] * 3
+    lib.hc_chi2_2x2_p.restype = d; lib.hc_chi2_2x2_p.argtypes = [d] * 4
+    lib.hc_logit_wald.restype = None
+    lib.hc_logit_wald.argtypes = [d] * 4 + [C.POINTER(d), C.POINTER(d)]
+    lib.hc_ks_prob_outside_square.restype = d; lib.hc_ks_prob_outside_square.argtypes = [ll, ll]
+    lib.hc_ks_equal_p.restype = d; lib.hc_ks_equal_p.argtypes = [ll, ll]
+    lib.hc_normal_two_sided.restype = d; lib.hc_normal_two_sided.argtypes = [d]
+    return lib
+
+
+def close_log10(got, want, rtol=1e-5, atol=1e-8):
+    if want == 0 or got == 0:
+        return want == got or max(want, got) < 1e-300
+    return abs(np.log10(got) - np.log10(want)) <= atol + rtol * abs(np.log10(want))
+
+
+def test_student_t(hc):
+    for df in [1, 1.7, 2.5, 5, 17.3, 60, 99.7, 198, 500, 5000, 19998]:
+        for t in [0, 1e-3, 0.1, 0.5, 1, 2, 3, 5, 8, 12, 20, 40, 80, 200, 1000]:
+            got, want = hc.hc_student_t_two_sided(t, df), 2 * stats.t.sf(t, df)
+            assert close_log10(got, want), (df, t, got, want)
+            assert hc.hc_student_t_two_sided(-t, df) == got
+
+
+def test_welch_against_scipy(hc):
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n0, n1 = rng.integers(2, 300, size=2)
+        a = rng.standard_normal(n0) * rng.uniform(0.5, 2) + rng.uniform(-1, 1)
+        b = rng.standard_normal(n1) * rng.uniform(0.5, 2)
+        want = stats.ttest_ind(a, b, equal_var=False).pvalue
+        got = hc.hc_welch_p(a.mean(), a.var(ddof=1), n0, b.mean(), b.var(ddof=1), n1)
+        assert close_log10(got, want), (n0, n1, got, want)
+
+
+def test_mwu_asymptotic_against_scipy(hc):
+    from oracle.nonparametric import mwu_stats
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        n0, n1 = rng.integers(9, 200, size=2)
+        a = np.round(rng.standard_normal(n0) * 4) / 4
+        b = np.round(rng.standard_normal(n1) * 4 + rng.uniform(-2, 2)) / 4
+        u2, tie, _, _ = mwu_stats(a, b)
+        want = stats.mannwhitneyu(a, b, alternative='two-sided').pvalue
+        assert close_log10(hc.hc_mwu_asymptotic_p(u2, tie, n0, n1), want)
+
+
+def test_mwu_exact_against_scipy(hc):
+    rng = np.random.default_rng(2)
+    for _ in range(300):
+        n0 = int(rng.integers(1, 9))
+        n1 = int(rng.integers(1, 40))
+        if rng.random() < 0.5:
+            n0, n1 = n1, n0
+        a = rng.standard_normal(n0)
+        b = rng.standard_normal(n1) + rng.uniform(-1, 1)
+        r = stats.mannwhitneyu(a, b, alternative='two-sided', method='exact')
+        u1 = int(r.statistic)
+        umin = min(u1, n0 * n1 - u1)
+        got = hc.hc_mwu_exact_p(umin, n0, n1)
+        assert close_log10(got, r.pvalue), (n0, n1, u1, got, r.pvalue)
+        # method='auto' picks the exact distribution here (no ties, a sample of <= 8 values)
+        assert stats.mannwhitneyu(a, b, alternative='two-sided').pvalue == r.pvalue
+
+
+def test_chi2_2x2_against_scipy(hc):
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        t = rng.integers(1, 300, size=(2, 2)).astype(float)
+        want = stats.chi2_contingency(t).pvalue
+        got = hc.hc_chi2_2x2_p(t[0, 0], t[0, 1], t[1, 0], t[1, 1])
+        assert close_log10(got, want), (t, got, want)
+
+
+def test_logit_wald_closed_form(hc):
+    """On a 2x2 table the logistic MLE is closed form: coef = ln(ad/bc), se^2 = sum 1/t."""
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        t = rng.integers(1, 400, size=(2, 2)).astype(float)
+        coef, p = C.c_double(), C.c_double()
+        hc.hc_logit_wald(t[0, 0], t[0, 1], t[1, 0], t[1, 1], C.byref(coef), C.byref(p))
+        want_coef = np.log(t[1, 1] * t[0, 0] / (t[1, 0] * t[0, 1]))
+        se = np.sqrt((1 / t).sum())
+        want_p = 2 * stats.norm.sf(abs(want_coef / se))
+        assert abs(coef.value - want_coef) < 1e-8 * max(1, abs(want_coef))
+        assert close_log10(p.value, want_p, rtol=1e-5, atol=1e-7)
+        from oracle.gmm_test import logit_wald
+        oc, op = logit_wald(t)
+        assert abs(oc - coef.value) < 1e-12 * max(1, abs(oc)) and close_log10(p.value, op)
+
+
+def test_ks_equal_sizes_bitwise(hc):
+    from scipy.stats._stats_py import _compute_prob_outside_square
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n = int(rng.integers(1, 3000))
+        h = int(rng.integers(1, n + 1))
+        assert hc.hc_ks_prob_outside_square(n, h) == _compute_prob_outside_square(n, h)
+
+
+def test_ks_equal_sizes_with_scipy_fallback(hc):
+    """Where SciPy's exact attempt 'fails' (Horner product rounds above 1) it reports the
+    one-sample Kolmogorov tail instead; ks_equal_p follows it to 4e-13."""
+    from oracle.ks_exact import ks_exact_p
+    hit = 0
+    for n in list(range(1, 420)) + [777, 1000, 2500, 5000]:
+        for h in range(1, min(n, 12) + 1):
+            want = ks_exact_p(n, n, h)
+            got = hc.hc_ks_equal_p(n, h)
+            from scipy.stats._stats_py import _compute_prob_outside_square
+            raw = _compute_prob_outside_square(n, h)
+            if not (0 <= raw <= 1):
+                hit += 1
+                assert abs(got - want) < 1e-12, (n, h, got, want)
+            else:
+                assert got == want, (n, h, got, want)
+    assert hit > 100
+    # the case the fallback is visible in: n0 = n1 = 7, D = 1/7
+    a = np.arange(7.0)
+    b = np.arange(7.0) + 0.5
+    assert abs(hc.hc_ks_equal_p(7, 1) - stats.ks_2samp(a, b).pvalue) < 1e-15

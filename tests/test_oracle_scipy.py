@@ -1,0 +1,75 @@
+"""The oracle's restatements of SciPy / statsmodels arithmetic against the real thing."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle.fdr import auto_qvalues, fdr_bh, multipletests_filter_nan
+from oracle.ks_exact import ks_exact_p, ks_h, outer_prob_inside_method, prob_outside_square
+from oracle.nonparametric import mwu_asymptotic_p, mwu_stats
+
+
+def test_ks_exact_matches_scipy_on_samples():
+    rng = np.random.default_rng(0)
+    exact = 0
+    for i in range(400):
+        n0, n1 = rng.integers(1, 120, size=2)
+        if i % 5 == 0:
+            n1 = n0
+        a = rng.standard_normal(n0)
+        b = rng.standard_normal(n1) + rng.uniform(-1, 1)
+        if i % 3 == 0:          # ties
+            a, b = np.round(a * 3) / 3, np.round(b * 3) / 3
+        h, _, _ = ks_h(a, b)
+        r = stats.ks_2samp(a, b)
+        g = np.gcd(n0, n1)
+        assert h == int(round(r.statistic * (n0 // g) * n1))
+        p = ks_exact_p(int(n0), int(n1), h)
+        assert abs(p - r.pvalue) <= 1e-12 * max(p, 1e-300) or abs(np.log10(p) - np.log10(r.pvalue)) < 1e-8
+        exact += p == r.pvalue
+    assert exact > 380
+
+
+def test_ks_inner_routines_bitwise():
+    from scipy.stats._stats_py import _compute_outer_prob_inside_method, _compute_prob_outside_square
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        m, n = rng.integers(1, 400, size=2)
+        g = int(np.gcd(m, n))
+        lcm = m // g * n
+        h = int(rng.integers(1, lcm + 1))
+        if m == n:
+            assert prob_outside_square(int(m), min(h, int(m))) == _compute_prob_outside_square(int(m), min(h, int(m)))
+        else:
+            assert outer_prob_inside_method(int(m), int(n), g, h) == _compute_outer_prob_inside_method(int(m), int(n), g, h)
+
+
+def test_mwu_statistics_and_p():
+    rng = np.random.default_rng(2)
+    for i in range(200):
+        n0, n1 = rng.integers(9, 150, size=2)
+        a = rng.standard_normal(n0)
+        b = rng.standard_normal(n1) + 0.3
+        if i % 2:
+            a, b = np.round(a * 2) / 2, np.round(b * 2) / 2
+        u2, tie, _, _ = mwu_stats(a, b)
+        r = stats.mannwhitneyu(a, b, alternative='two-sided')
+        assert u2 == int(round(2 * r.statistic))
+        assert abs(mwu_asymptotic_p(u2, tie, n0, n1) - r.pvalue) <= 1e-12 * r.pvalue + 1e-300
+
+
+def test_bh_known_answer_of_the_reference():
+    # /root/reference/tests/test_postprocessing.py:18-24
+    p = np.array([0.1, 0.01, np.nan, 0.01, 0.5, 0.4, 0.01, 0.001, np.nan, np.nan, 0.01, np.nan])
+    want = np.array([0.13333333, 0.016, np.nan, 0.016, 0.5, 0.45714286, 0.016, 0.008, np.nan, np.nan, 0.016, np.nan])
+    assert np.allclose(multipletests_filter_nan(p), want, equal_nan=True)
+
+
+def test_bh_properties():
+    rng = np.random.default_rng(3)
+    p = rng.uniform(size=1000) ** 2
+    q = fdr_bh(p)
+    order = np.argsort(p)
+    assert (np.diff(q[order]) >= 0).all() and (q >= p).all() and (q <= 1).all()
+    assert stats.false_discovery_control(p, method='bh') == pytest.approx(q, rel=1e-12)
+    a = auto_qvalues(np.array([0.01, 0.5, np.nan, 0.2]), np.array(['KS', 'GMM', 'KS', 'KS']))
+    assert np.isnan(a[2]) and a[1] == pytest.approx(0.5 * 4)

@@ -1,0 +1,71 @@
+"""Transcript sharding (LPT) and the end-of-run gather, on CPU with gloo, world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nanocompore_b200.sharding import gather_columns, lpt_partition, work_estimate
+
+
+def test_lpt_partition_is_deterministic_and_balanced():
+    rng = np.random.default_rng(0)
+    P = rng.integers(500, 4000, size=400)
+    n = np.where(rng.random(400) < 0.05, 10000, rng.integers(60, 400, size=400))
+    w = work_estimate(P, n)
+    a = lpt_partition(w, 8)
+    b = lpt_partition(w, 8)
+    assert all((x == y).all() for x, y in zip(a, b))
+    assert sorted(np.concatenate(a).tolist()) == list(range(400))
+    loads = np.array([w[s].sum() for s in a])
+    assert loads.max() / loads.mean() < 1.05
+    assert all((np.diff(s) > 0).all() for s in a)
+
+
+def test_lpt_partition_edge_cases():
+    assert [s.tolist() for s in lpt_partition([], 2)] == [[], []]
+    assert [s.tolist() for s in lpt_partition([5.0], 3)] == [[0], [], []]
+    assert [s.tolist() for s in lpt_partition([1, 1, 1, 1], 2)] == [[0, 2], [1, 3]]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    work = np.array([10, 30, 20, 5, 25, 15, 40], dtype=float)
+    shard = lpt_partition(work, world)[rank]
+    # rows of the shard: 3 positions per transcript, 2 result columns
+    keys = torch.tensor([(int(t) << 32) | p for t in shard for p in range(3)], dtype=torch.int64)
+    cols = torch.stack([keys.to(torch.float64) * 0.5, torch.full((keys.numel(),), float(rank), dtype=torch.float64)])
+    if rank == 1:
+        cols[0, 0] = float('nan')
+    res = gather_columns(cols, keys)
+    if rank == 0:
+        c, k = res
+        torch.save({'cols': c, 'keys': k}, out)
+    else:
+        assert res is None
+    dist.destroy_process_group()
+
+
+def test_gather_columns_gloo_world2(tmp_path):
+    out = str(tmp_path / 'gathered.pt')
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    keys = got['keys'].numpy()
+    assert (np.diff(keys) > 0).all() and keys.size == 21
+    expect = np.array([(t << 32) | p for t in range(7) for p in range(3)])
+    assert (keys == expect).all()
+    c0 = got['cols'][0].numpy()
+    nan = np.isnan(c0)
+    assert nan.sum() == 1
+    assert (c0[~nan] == keys[~nan] * 0.5).all()
