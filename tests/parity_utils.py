@@ -21,8 +21,10 @@ def assert_pvalues_close(got, want, what=''):
         f"{what}: NaN pattern differs at {np.nonzero(nan_g != nan_w)[0][:10]}"
     ok = ~nan_w
     g, w = got[ok], want[ok]
-    zero = (w == 0) | (g == 0)
-    assert ((g == 0) == (w == 0))[zero].all() if zero.any() else True, f"{what}: zero pattern differs"
+    # below 1e-300 the tails are denormal or flushed to 0 depending on the erfc at hand
+    zero = (w < 1e-300) | (g < 1e-300)
+    assert ((g < 1e-300) == (w < 1e-300))[zero].all() if zero.any() else True, \
+        f"{what}: underflow pattern differs"
     g, w = g[~zero], w[~zero]
     lg, lw = np.log10(g), np.log10(w)
     bad = ~np.isclose(lg, lw, rtol=LOG10P_RTOL, atol=LOG10P_ATOL)

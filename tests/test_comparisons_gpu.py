@@ -149,7 +149,8 @@ def test_auto_routes_by_coverage():
     rng = np.random.default_rng(2)
     n = 520
     data = rng.standard_normal((4, 2 * n, 2)).astype(np.float32)
-    data[:2, 100:, :] = np.nan          # positions 0,1: 100 reads -> KS; positions 2,3: 1040 -> GMM
+    data[:2, 50:n, :] = np.nan          # positions 0,1: 50 + 50 reads -> KS;
+    data[:2, n + 50:, :] = np.nan       # positions 2,3: 1040 reads -> GMM
     df = compare(config(comparison_methods=['auto']), data, np.repeat([0, 1, 2, 3], n // 2),
                  np.repeat([0, 1], n), np.arange(4, dtype=np.int16))
     assert df['auto_test'].tolist() == ['KS', 'KS', 'GMM', 'GMM']
