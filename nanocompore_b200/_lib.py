@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libncb.so')
+# NCB_LIB_PATH lets a tuning run load an experimental build of the same ABI
+LIB_PATH = os.environ.get('NCB_LIB_PATH') or os.path.join(HERE, 'libncb.so')
 
 NCB_ABI_VERSION = 1
 NCB_MAX_READS = 10240
@@ -72,19 +73,20 @@ class NcbError(RuntimeError):
         self.code = code
 
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Loads libncb.so (built in-tree by ``python -m nanocompore_b200.build``)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(path=None):
+    """Loads libncb.so (built in-tree by ``python -m nanocompore_b200.build``).  ``path`` selects
+    another build of the same ABI (tuning runs)."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m nanocompore_b200.build` "
+            f"{path} is missing: build it with `python -m nanocompore_b200.build` "
             "(nanocompore_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.ncb_abi_version.restype = C.c_int
     lib.ncb_default_opts.argtypes = [C.POINTER(NcbOpts)]
@@ -116,7 +118,7 @@ def load():
     lib.ncb_timing_totals.restype = C.c_int
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 

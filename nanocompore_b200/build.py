@@ -42,7 +42,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), lib=None, objdir=None):
+    """``defines`` / ``lib`` / ``objdir`` build an experimental variant next to the product
+    library (tuning runs select it with NCB_LIB_PATH)."""
+    global OBJDIR, LIB
+    if lib:
+        LIB = lib
+    if objdir:
+        OBJDIR = objdir
     os.makedirs(OBJDIR, exist_ok=True)
     exe = nvcc()
     jobs = []
@@ -52,7 +59,8 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJDIR, src.replace('.cu', '.o'))
         objs.append(o)
         if force or _stale(o, [s] + HEADERS):
-            cmd = [exe] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+            cmd = [exe] + NVCC_FLAGS + ['-D' + d for d in defines] + \
+                (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -71,4 +79,11 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    out = [a.split('=', 1)[1] for a in sys.argv[1:] if a.startswith('--out=')]
+    if out:
+        tag = os.path.splitext(os.path.basename(out[0]))[0]
+        print(build(force=True, verbose='-v' in sys.argv, defines=defs, lib=os.path.abspath(out[0]),
+                    objdir=os.path.join(ROOT, 'build', tag)))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs))

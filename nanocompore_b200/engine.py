@@ -150,10 +150,10 @@ class Engine:
 
     def __init__(self, device=0, *, tests=('GMM', 'KS'), n_samples=4, depleted_condition=0,
                  min_coverage=0, dwell_is_raw=False, cluster_counts='hard', with_logit=False,
-                 em_max_iter=100, em_tol=1e-3, reg_covar=1e-6):
+                 em_max_iter=100, em_tol=1e-3, reg_covar=1e-6, lib_path=None):
         if not torch.cuda.is_available():
             raise RuntimeError("nanocompore_b200 needs a CUDA device: there is no CPU fallback")
-        self.lib = L.load()
+        self.lib = L.load(lib_path)
         if isinstance(device, str):
             device = torch.device(device)
         if isinstance(device, torch.device):
