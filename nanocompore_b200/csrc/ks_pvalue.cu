@@ -9,8 +9,10 @@
 //             paths (0,0)->(m,n) that leave the band |i/m - j/n| < h/lcm,
 //                 C(i,j) = (C(i-1,j)*i + C(i,j-1)*j) / (i+j),   C = 1 outside the band,
 //             C(0,j) = 0 inside the band; the answer is C(m,n).
-// Every cell is computed with the same three IEEE operations SciPy performs (no FMA
-// contraction, true division), so the result does not depend on how the cells are scheduled.
+// Every cell is computed with the IEEE operations SciPy performs (two products and a sum
+// without contraction, and a correctly rounded quotient -- obtained from a correctly rounded
+// reciprocal plus one exact-remainder correction, see div_by_recip), so the result does not
+// depend on how the cells are scheduled and is bitwise SciPy's.
 //
 // The recurrence is sequential along a row, so problems are binned by kind and cost:
 //   SMALL  window <= 64 cells: one thread per problem, its window in shared memory
@@ -33,6 +35,8 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b) {  //
 __device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   // a >= 0, b > 0
     return (a + b - 1) / b;
 }
+
+#define KS_RECIP_TABLE 1024    /* reciprocals of i + j: SMALL problems have n0 + n1 < this */
 
 struct KsProblem {
     int m, n;            // m >= n
@@ -77,7 +81,7 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
             long long maxj0 = min(ceildiv_ll(k.h, k.mg), (long long)k.n + 1);
             long long lenA = min(2 * maxj0 + 2, (long long)k.n + 1);
             double width = fmin(2.0 * (double)k.h / (double)k.mg + 1.0, (double)k.n + 1.0);
-            int kind = lenA <= NCB_KS_SMALL_WINDOW ? NCB_KS_KIND_SMALL
+            int kind = (lenA <= NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) ? NCB_KS_KIND_SMALL
                        : (k.n <= NCB_KS_LARGE_MAXN ? NCB_KS_KIND_LARGE : NCB_KS_KIND_HUGE);
             bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
         }
@@ -117,44 +121,62 @@ __global__ void ks_scatter_kernel(int64_t nprob, NcbKsWork w) {
     }
 }
 
+// a / b for an integer-valued b with r = RN(1/b): q = RN(a r), then one correction through the
+// exact remainder.  With a correctly rounded reciprocal this IS the correctly rounded quotient
+// (Markstein), i.e. the same bits as SciPy's true division, for 3 fp64 operations instead of
+// the ~12 of a division.  (Not valid in the denormal range, p < 1e-290.)
+__device__ __forceinline__ double div_by_recip(double a, double b, double r) {
+    const double q = __dmul_rn(a, r);
+    const double rem = __fma_rn(-q, b, a);
+    return __fma_rn(rem, r, q);
+}
+
 // ---- thread per problem: unequal sizes, small window ------------------------------------
 #define KS_SMALL_THREADS 128
 __global__ void __launch_bounds__(KS_SMALL_THREADS)
 ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out,
                 NcbKsWork w) {
-    extern __shared__ double A_all[];   // [NCB_KS_SMALL_WINDOW][KS_SMALL_THREADS]
+    extern __shared__ double A_all[];   // [NCB_KS_SMALL_WINDOW][KS_SMALL_THREADS] + reciprocals
+    double *rtab = A_all + NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS;
     const int lo = w.hist[NCB_KS_KIND_SMALL * NCB_KS_BUCKETS];
     const int hi = w.hist[(NCB_KS_KIND_SMALL + 1) * NCB_KS_BUCKETS];
+    if (lo + (int)blockIdx.x * KS_SMALL_THREADS >= hi) return;   // whole block idle
+    for (int b = threadIdx.x; b < KS_RECIP_TABLE; b += KS_SMALL_THREADS)
+        rtab[b] = b ? __drcp_rn((double)b) : 0.0;
+    __syncthreads();
     const int idx = lo + blockIdx.x * KS_SMALL_THREADS + threadIdx.x;
     if (idx >= hi) return;
     const int q = w.list[idx];
     const KsProblem k = make_problem(n0[q], n1[q], h[q]);
     double *A = A_all + threadIdx.x;
 #define AT(j) A[(j) * KS_SMALL_THREADS]
-    const long long n = k.n, m = k.m, mg = k.mg, ng = k.ng, hh = k.h;
-    long long minj = 0, maxj = min(ceildiv_ll(hh, mg), n + 1);
-    long long curlen = maxj - minj;
+    const int n = k.n, m = k.m;
+    const long long mg = k.mg, ng = k.ng, hh = k.h;
+    int minj = 0, maxj = (int)min(ceildiv_ll(hh, mg), (long long)n + 1);
+    int curlen = maxj - minj;
     for (int j = 0; j < NCB_KS_SMALL_WINDOW; ++j) AT(j) = (j < maxj) ? 0.0 : 1.0;
     double result = -1.0;
-    for (long long i = 1; i <= m; ++i) {
-        const long long lastminj = minj, lastlen = curlen;
-        minj = max(floordiv_ll(ng * i - hh, mg) + 1, 0LL);
-        minj = min(minj, n);
-        maxj = min(ceildiv_ll(ng * i + hh, mg), n + 1);
+    for (int i = 1; i <= m; ++i) {
+        const int lastminj = minj, lastlen = curlen;
+        minj = (int)min(max(floordiv_ll(ng * i - hh, mg) + 1, 0LL), (long long)n);
+        maxj = (int)min(ceildiv_ll(ng * i + hh, mg), (long long)n + 1);
         if (maxj <= minj) { result = 1.0; break; }
         double val = (minj == 0) ? 0.0 : 1.0;
         const double di = (double)i;
-        const int shift = (int)(minj - lastminj);
-        const int len = (int)(maxj - minj);
+        const int shift = minj - lastminj;
+        const int len = maxj - minj;
+        double dj = (double)minj;
+        const double *rt = rtab + i + minj;
         for (int jj = 0; jj < len; ++jj) {
-            const long long j = jj + minj;
             const int src = jj + shift;
             const double up = (src < NCB_KS_SMALL_WINDOW) ? AT(src) : 1.0;
-            val = NCB_DDIV(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(val, (double)j)), (double)(i + j));
+            const double num = NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(val, dj));
+            val = div_by_recip(num, di + dj, rt[jj]);
             AT(jj) = val;
+            dj += 1.0;
         }
         curlen = len;
-        for (long long jj = curlen; jj < lastlen; ++jj) AT(jj) = 1.0;
+        for (int jj = curlen; jj < lastlen; ++jj) AT(jj) = 1.0;
     }
     if (result < 0.0) result = AT(maxj - minj - 1);
 #undef AT
@@ -207,6 +229,9 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
             const int nsteps = (jhi - jlo) + rows - 1;
             for (int t = 0; t < nsteps; ++t) {
                 const int j = jlo + t - lane;
+                // i + j = i0 + jlo + t on every lane: one reciprocal per step for the warp
+                const double den = (double)(i0 + jlo + t);
+                const double rden = __drcp_rn(den);
                 const double up_sh = __shfl_up_sync(0xffffffffu, cur, 1);
                 const bool act = row_on && j >= jlo && j < jhi;
                 if (act) {
@@ -214,8 +239,8 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
                     const long long v = ngi - mg * j;
                     double val = 1.0;
                     if ((v < 0 ? -v : v) < hh)
-                        val = NCB_DDIV(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, (double)j)),
-                                       (double)(i + j));
+                        val = div_by_recip(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, (double)j)),
+                                           den, rden);
                     cur = val;
                     left = val;
                     if (lane == rows - 1) prev[j] = val;
@@ -238,7 +263,7 @@ static const int KS_HUGE_WARPS = 4, KS_HUGE_BUF = NCB_MAX_READS / 2 + 1;
 int ncb_configure_ks_kernels(void) {
     cudaError_t e;
     e = cudaFuncSetAttribute(ks_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS * (int)sizeof(double));
+                             (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE) * (int)sizeof(double));
     if (e != cudaSuccess) return -1;
     e = cudaFuncSetAttribute(ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -269,7 +294,8 @@ int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, c
             n0, n1, h, p_out, w, NCB_KS_KIND_LARGE);
     int tblocks = (int)((nprob + KS_SMALL_THREADS - 1) / KS_SMALL_THREADS);
     ks_small_kernel<<<tblocks, KS_SMALL_THREADS,
-                      NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS * sizeof(double), s>>>(n0, n1, h, p_out, w);
+                      (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE) * sizeof(double), s>>>(
+        n0, n1, h, p_out, w);
     ks_equal_kernel<<<tblocks, KS_SMALL_THREADS, 0, s>>>(n0, h, p_out, w);
     return cudaGetLastError() == cudaSuccess ? 7 : -1;
 }
