@@ -12,7 +12,7 @@ namespace ncb {
 typedef unsigned long long u64;
 
 #define NCB_FULL 0xffffffffu
-#define NCB_RED_MAX 12   /* most 64-bit values reduced in one call */
+#define NCB_RED_MAX 16   /* most 64-bit values reduced in one call */
 
 struct OpAddF64 { typedef double T; __device__ static T id() { return 0.0; }
                   __device__ static T f(T a, T b) { return a + b; } };
