@@ -13,6 +13,9 @@ typedef unsigned long long u64;
 
 #define NCB_FULL 0xffffffffu
 #define NCB_RED_MAX 16   /* most 64-bit values reduced in one call */
+#define NCB_RED_STRIDE 13 /* row stride of a warp group's reduction scratch (odd: no bank conflicts);
+                             warp groups reduce at most 13 values at once */
+#define NCB_RED_WARP_WORDS (32 * NCB_RED_STRIDE + 16)   /* 64-bit words of scratch per warp group */
 
 struct OpAddF64 { typedef double T; __device__ static T id() { return 0.0; }
                   __device__ static T f(T a, T b) { return a + b; } };
@@ -37,7 +40,7 @@ __device__ __forceinline__ u64 shfl_idx_t(u64 v, int l) { return __shfl_sync(NCB
 template <int GROUP>
 struct Grp {
     static constexpr int NW = GROUP / 32;
-    u64 *red;     // CTA groups: [2][32][NCB_RED_MAX] scratch; warp groups: unused
+    u64 *red;     // CTA groups: [2][32][NCB_RED_MAX] scratch; warp groups: [NCB_RED_WARP_WORDS]
     int phase;
     int tid;      // thread index inside the group
     int lane, warp;
@@ -51,10 +54,44 @@ struct Grp {
         if (GROUP == 32) __syncwarp(); else __syncthreads();
     }
 
-    // all-reduce NV values with Op; result in v[] on every thread
+    // all-reduce NV values with Op; result in v[] on every thread.
+    // Warp groups with more than two values go through the group's shared-memory scratch
+    // (red: [32][NCB_RED_STRIDE] partials + [16] results): every lane stores its NV partials,
+    // lane l folds column l % 16 over 16 rows in a fixed order, the two half-warps are combined
+    // with one shuffle and the NV results are read back by all lanes -- about 2 NV + 45
+    // instructions where a butterfly of 64-bit shuffles costs about 30 NV.
     template <class Op, int NV>
     __device__ __forceinline__ void all_reduce(typename Op::T (&v)[NV]) {
         typedef typename Op::T T;
+        static_assert(NV <= NCB_RED_MAX, "too many values in one reduction");
+        if (GROUP == 32 && NV > 2) {
+            T *buf = reinterpret_cast<T *>(red);
+            T *res = buf + 32 * NCB_RED_STRIDE;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) buf[lane * NCB_RED_STRIDE + i] = v[i];
+            __syncwarp();
+            const int c = lane & 15;
+            const T *col = buf + (lane & 16) * NCB_RED_STRIDE + c;
+            T acc = Op::id();
+            if (c < NV) {
+                T a0 = Op::f(Op::f(col[0 * NCB_RED_STRIDE], col[1 * NCB_RED_STRIDE]),
+                             Op::f(col[2 * NCB_RED_STRIDE], col[3 * NCB_RED_STRIDE]));
+                T a1 = Op::f(Op::f(col[4 * NCB_RED_STRIDE], col[5 * NCB_RED_STRIDE]),
+                             Op::f(col[6 * NCB_RED_STRIDE], col[7 * NCB_RED_STRIDE]));
+                T a2 = Op::f(Op::f(col[8 * NCB_RED_STRIDE], col[9 * NCB_RED_STRIDE]),
+                             Op::f(col[10 * NCB_RED_STRIDE], col[11 * NCB_RED_STRIDE]));
+                T a3 = Op::f(Op::f(col[12 * NCB_RED_STRIDE], col[13 * NCB_RED_STRIDE]),
+                             Op::f(col[14 * NCB_RED_STRIDE], col[15 * NCB_RED_STRIDE]));
+                acc = Op::f(Op::f(a0, a1), Op::f(a2, a3));
+            }
+            acc = Op::f(acc, shfl_xor_t(acc, 16));
+            if (lane < NV) res[lane] = acc;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] = res[i];
+            __syncwarp();
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
 #pragma unroll
