@@ -26,7 +26,7 @@ struct ncb_handle {
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
-    DevBuf ks_n0, ks_n1, ks_h;
+    DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n;
     DevBuf wl_count, wl_list;
     DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch;
     DevBuf fdr_scratch, fdr_p, fdr_q;
@@ -166,7 +166,7 @@ void ncb_destroy(ncb_handle *h) {
     cudaSetDevice(h->device);
     DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
                      &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
-                     &h->ks_h, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
+                     &h->ks_h, &h->zbuf, &h->gmm_n, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
                      &h->kw_bin, &h->kw_fetch, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d};
     for (DevBuf *b : all) release(*b);
@@ -305,6 +305,12 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     a.ks_n0 = (int32_t *)h->ks_n0.ptr;
     a.ks_n1 = (int32_t *)h->ks_n1.ptr;
     a.ks_h = (int64_t *)h->ks_h.ptr;
+    if (o.tests & (NCB_TEST_GMM | NCB_TEST_AUTO)) {
+        ENSURE(h->zbuf, (size_t)E * sizeof(float2));
+        ENSURE(h->gmm_n, (size_t)P * sizeof(int32_t));
+        a.zbuf = (float2 *)h->zbuf.ptr;
+        a.gmm_n = (int32_t *)h->gmm_n.ptr;
+    }
     ENSURE(h->wl_count, NCB_NUM_CLASSES * sizeof(int32_t));
     ENSURE(h->wl_list, (size_t)P * NCB_NUM_CLASSES * sizeof(int32_t));
     NcbWorklists wl;

@@ -30,6 +30,9 @@ struct NcbDeviceArgs {
     uint32_t *counts;
     int64_t *diag_i64;
     double *diag_f64;
+    // scratch: hand-over from the statistics kernel to the mixture kernel
+    float2 *zbuf;                // standardised (intensity, dwell) per entry, NaN x = not in the fit
+    int32_t *gmm_n;              // [P] reads in the fit, 0 = no mixture test on this position
     // scratch: exact-KS work items, one per (variable, position): index v * P + p
     int32_t *ks_n0;
     int32_t *ks_n1;
