@@ -317,26 +317,37 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (position kernel), HBM bound --------------------
-    # algorithmic bytes per launch: every read once (8 B signal + 1 B label), the CSR offsets,
-    # and the result columns written once per position
-    out_bytes_per_pos = 4 + 8 * L.NCB_PV_ROWS + 4 * L.NCB_ST_ROWS + 4 * 2 * 4 + (4 + 4 + 8) * 2
-    alg_bytes = entries * 9 + P * (8 + out_bytes_per_pos)
-    ms_pos = totals['ms_position'] / max(totals['batches'], 1)
+    # ---- roofline of the dominant kernel (the mixture kernel), HBM bound -------------------
+    # algorithmic bytes per launch of the mixture kernel: standardised values (8 B) + label
+    # (1 B) of every read once, offsets + read count (12 B) and the columns it writes
+    # (chi2 p, LOR, 2 x 4 cluster counts = 44 B) per position.  The statistics kernel moves
+    # 9 B/read in and 8 B/read out plus 8 + 132 B per position.
+    nb = max(totals['batches'], 1)
+    gmm_bytes = entries * 9 + P * (12 + 44)
+    stats_bytes = entries * (9 + 8) + P * (8 + 132)
+    ms_gmm, ms_stats = totals['ms_gmm'] / nb, totals['ms_stats'] / nb
     peak, peak_src = measured_peaks()
-    achieved = alg_bytes / (ms_pos / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "position_kernel_warp<256,8>", "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
-                "ms_per_launch": ms_pos,
-                "ms_ks_pvalue_kernels": totals['ms_ks'] / max(totals['batches'], 1),
-                "ms_classify": totals['ms_classify'] / max(totals['batches'], 1),
-                "note": "the kernel is fp64-pipe bound (EM in fp64), not HBM bound; see DESIGN.md"}
+    achieved = gmm_bytes / (ms_gmm / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "position_kernel_warp<256,8,2,true> (mixture kernel)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": gmm_bytes, "ms_per_launch": ms_gmm,
+                "statistics_kernel": {"kernel": "position_kernel_warp<256,8,3,false>",
+                                      "algorithmic_bytes_per_launch": stats_bytes, "ms_per_launch": ms_stats,
+                                      "achieved": stats_bytes / (ms_stats / 1000.0) / 1e9,
+                                      "frac": stats_bytes / (ms_stats / 1000.0) / 1e9 / peak},
+                "ms_ks_pvalue_kernels": totals['ms_ks'] / nb,
+                "ms_classify": totals['ms_classify'] / nb,
+                "note": "both kernels are issue / fp64-pipe bound (fp64 EM, sort), not HBM bound: "
+                        "DRAM traffic equals the algorithmic bytes and is ~1 % of peak; see DESIGN.md"}
     ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(ncu_traffic):
         try:
             with open(ncu_traffic) as f:
-                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                tr = json.load(f)
+            # ncu capture at tr['positions'] positions per launch: scale per position
+            roofline["traffic"] = tr["dram_bytes_per_position"] * P
+            roofline["traffic_source"] = tr.get("source")
         except Exception:
             pass
 

@@ -224,9 +224,10 @@ int ncb_set_timing(ncb_handle *h, int enabled);
 int ncb_last_timing(ncb_handle *h, float *ms_position_kernels, float *ms_ks_kernels, float *ms_total);
 /* Sums over every ncb_compare since the last ncb_set_timing(h, 1): number of batches and the
  * device milliseconds (CUDA events on the caller's stream) of the staging copy + classification,
- * of the position kernels and of the KS p-value kernels.  Blocks until those batches are done. */
-int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_position,
-                      double *ms_ks);
+ * of the statistics kernels, of the mixture kernels and of the KS p-value kernels.  Blocks until
+ * those batches are done. */
+int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_stats,
+                      double *ms_gmm, double *ms_ks);
 
 #ifdef __cplusplus
 }

@@ -113,8 +113,7 @@ def load(path=None):
     lib.ncb_set_timing.restype = C.c_int
     lib.ncb_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.ncb_last_timing.restype = C.c_int
-    lib.ncb_timing_totals.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double),
-                                      C.POINTER(C.c_double)]
+    lib.ncb_timing_totals.argtypes = [vp, C.POINTER(i64)] + [C.POINTER(C.c_double)] * 4
     lib.ncb_timing_totals.restype = C.c_int
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")

@@ -20,9 +20,9 @@ struct ncb_handle {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // events of the last timed batch
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // events of the last timed batch
     bool timed = false;
-    std::vector<cudaEvent_t> ev_log;   // 4 events per timed batch since ncb_set_timing(h, 1)
+    std::vector<cudaEvent_t> ev_log;   // 5 events per timed batch since ncb_set_timing(h, 1)
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
@@ -239,7 +239,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
 
     const bool time_it = h->timing != 0;
     if (time_it) {
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 5; ++i) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             h->ev_log.push_back(e);
@@ -329,17 +329,17 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     if (n < 0) return fail(h, NCB_ERR_CUDA, "classify launch", cudaGetLastError());
     h->launches += n;
     if (time_it) CK(cudaEventRecord(h->ev[1], s));
-    n = ncb_launch_position_kernels(a, wl, h->sm_count, s);
+    n = ncb_launch_position_kernels(a, wl, h->sm_count, s, time_it ? h->ev[2] : nullptr);
     if (n < 0) return fail(h, NCB_ERR_CUDA, "position kernel launch", cudaGetLastError());
     h->launches += n;
-    if (time_it) CK(cudaEventRecord(h->ev[2], s));
+    if (time_it) CK(cudaEventRecord(h->ev[3], s));
     if (any_ks) {
         // rows NCB_PV_KS_INTENSITY, NCB_PV_KS_DWELL are the first two rows of pvalues: [2][P]
         n = ncb_launch_ks_pvalues(2 * P, a.ks_n0, a.ks_n1, a.ks_h, a.pvalues, kw, h->sm_count, s);
         if (n < 0) return fail(h, NCB_ERR_CUDA, "KS p-value launch", cudaGetLastError());
         h->launches += n;
     }
-    if (time_it) CK(cudaEventRecord(h->ev[3], s));
+    if (time_it) CK(cudaEventRecord(h->ev[4], s));
     h->timed = time_it;
 
     // ---- results -----------------------------------------------------------------------
@@ -446,25 +446,27 @@ int ncb_set_timing(ncb_handle *h, int enabled) {
     return NCB_OK;
 }
 
-int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_position,
-                      double *ms_ks) {
+int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_stats,
+                      double *ms_gmm, double *ms_ks) {
     if (!h) return NCB_ERR_INVALID;
     CK(cudaSetDevice(h->device));
-    double a = 0, b = 0, c = 0;
-    const size_t nb = h->ev_log.size() / 4;
+    double a = 0, b = 0, c = 0, d = 0;
+    const size_t nb = h->ev_log.size() / 5;
     for (size_t i = 0; i < nb; ++i) {
-        cudaEvent_t *e = &h->ev_log[4 * i];
-        CK(cudaEventSynchronize(e[3]));
-        float x = 0, y = 0, z = 0;
+        cudaEvent_t *e = &h->ev_log[5 * i];
+        CK(cudaEventSynchronize(e[4]));
+        float x = 0, y = 0, z = 0, w = 0;
         CK(cudaEventElapsedTime(&x, e[0], e[1]));
         CK(cudaEventElapsedTime(&y, e[1], e[2]));
         CK(cudaEventElapsedTime(&z, e[2], e[3]));
-        a += x; b += y; c += z;
+        CK(cudaEventElapsedTime(&w, e[3], e[4]));
+        a += x; b += y; c += z; d += w;
     }
     if (n_batches) *n_batches = (int64_t)nb;
     if (ms_classify) *ms_classify = a;
-    if (ms_position) *ms_position = b;
-    if (ms_ks) *ms_ks = c;
+    if (ms_stats) *ms_stats = b;
+    if (ms_gmm) *ms_gmm = c;
+    if (ms_ks) *ms_ks = d;
     return NCB_OK;
 }
 
@@ -472,11 +474,11 @@ int ncb_last_timing(ncb_handle *h, float *ms_position, float *ms_ks, float *ms_t
     if (!h) return NCB_ERR_INVALID;
     if (!h->timed) return fail(h, NCB_ERR_INVALID, "ncb_last_timing: the last ncb_compare was not timed");
     CK(cudaSetDevice(h->device));
-    CK(cudaEventSynchronize(h->ev[3]));
+    CK(cudaEventSynchronize(h->ev[4]));
     float a = 0, b = 0, c = 0;
-    CK(cudaEventElapsedTime(&a, h->ev[1], h->ev[2]));
-    CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
-    CK(cudaEventElapsedTime(&c, h->ev[0], h->ev[3]));
+    CK(cudaEventElapsedTime(&a, h->ev[1], h->ev[3]));
+    CK(cudaEventElapsedTime(&b, h->ev[3], h->ev[4]));
+    CK(cudaEventElapsedTime(&c, h->ev[0], h->ev[4]));
     if (ms_position) *ms_position = a;
     if (ms_ks) *ms_ks = b;
     if (ms_total) *ms_total = c;

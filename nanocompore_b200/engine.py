@@ -326,6 +326,8 @@ class Engine:
 
     def timing_totals(self):
         """Sums of the CUDA-event timings of every batch since ``set_timing(True)``."""
-        n, a, b, c = C.c_int64(), C.c_double(), C.c_double(), C.c_double()
-        self._check(self.lib.ncb_timing_totals(self._handle, C.byref(n), C.byref(a), C.byref(b), C.byref(c)))
-        return dict(batches=n.value, ms_classify=a.value, ms_position=b.value, ms_ks=c.value)
+        n, a, b, c, d = C.c_int64(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.ncb_timing_totals(self._handle, C.byref(n), C.byref(a), C.byref(b),
+                                               C.byref(c), C.byref(d)))
+        return dict(batches=n.value, ms_classify=a.value, ms_stats=b.value, ms_gmm=c.value,
+                    ms_position=b.value + c.value, ms_ks=d.value)
