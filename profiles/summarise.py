@@ -54,59 +54,86 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 
 
+UNITS = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+
+
+def short_name(name):
+    base = name.split('(')[0].replace('void ', '').split('::')[-1]
+    return base.replace('<', '_').replace('>', '').replace(', ', '_').replace(' ', '').replace('(int)', '').replace('(bool)', '')
+
+
 def full(tag, rep):
+    """One summary file per distinct kernel captured in the report (last capture of each)."""
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    h, units, v = rows[0], rows[1], rows[-1]
-    name = v[h.index('Kernel Name')]
-    out = [f"# {tag}: `{name[:100]}` (ncu --set full --clock-control none)", "", "| metric | value | unit |", "|---|---:|---|"]
-    for w in WANT:
-        if w in h:
-            i = h.index(w)
-            out.append(f"| {w} | {v[i]} | {units[i]} |")
+    h, units = rows[0], rows[1]
+    kernels = collections.OrderedDict()
+    for v in rows[2:]:
+        kernels[v[h.index('Kernel Name')]] = v
     src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(src.splitlines()))
-    hh = rows[1]
-    si, ii, wi = hh.index('Source'), hh.index('Instructions Executed'), hh.index('Warp Stall Sampling (All Samples)')
-    stall_cols = [i for i, n in enumerate(hh) if n.startswith('stall_') and 'Not Issued' not in n]
-    ops, samp, stalls = collections.Counter(), collections.Counter(), collections.Counter()
-    tot = tots = 0.0
-    nsass = 0
-    for r in rows[2:]:
-        if len(r) < len(hh):
-            continue
-        op = r[si].split()
-        if not op:
-            continue
-        nsass += 1
-        nm = (op[1] if op[0].startswith('@') else op[0]).split('.')[0]
-        n, s = float(r[ii] or 0), float(r[wi] or 0)
-        ops[nm] += n
-        samp[nm] += s
-        tot += n
-        tots += s
-        for c in stall_cols:
-            stalls[hh[c]] += float(r[c] or 0)
-    out += ["", f"SASS instructions in the kernel: {nsass}; warp instructions executed: {tot:.0f}", "",
-            "| opcode | % of executed | % of stall samples |", "|---|---:|---:|"]
-    for k, n in ops.most_common(14):
-        out.append(f"| {k} | {100 * n / tot:.1f} | {100 * samp[k] / max(tots, 1):.1f} |")
-    out += ["", "| stall reason | % of samples |", "|---|---:|"]
-    for k, n in stalls.most_common(8):
-        out.append(f"| {k} | {100 * n / max(tots, 1):.1f} |")
-    short = name.split('(')[0].split('::')[-1].replace('<', '_').replace('>', '').replace(', ', '_').replace(' ', '')
-    open(os.path.join(HERE, f'{tag}_{short}.md'), 'w').write('\n'.join(out) + '\n')
-    # per-launch DRAM traffic for bench.py's roofline.traffic
-    try:
-        rd = float(v[h.index('dram__bytes_read.sum')]) * {'Mbyte': 1e6, 'Kbyte': 1e3, 'Gbyte': 1e9, 'byte': 1}[units[h.index('dram__bytes_read.sum')]]
-        wr = float(v[h.index('dram__bytes_write.sum')]) * {'Mbyte': 1e6, 'Kbyte': 1e3, 'Gbyte': 1e9, 'byte': 1}[units[h.index('dram__bytes_write.sum')]]
-        return name, rd + wr
-    except Exception:
-        return name, None
+    srows = list(csv.reader(src.splitlines()))
+    sections = collections.OrderedDict()
+    cur = None
+    for r in srows:
+        if r and r[0] == 'Kernel Name':
+            cur = r[1]
+            sections[cur] = []
+        elif cur is not None:
+            sections[cur].append(r)
+    out_traffic = {}
+    for name, v in kernels.items():
+        out = [f"# {tag}: `{name[:110]}` (ncu --set full --clock-control none)", "", "| metric | value | unit |", "|---|---:|---|"]
+        for w in WANT + ['sm__icc_request_hit_rate.pct', 'gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed',
+                         'smsp__warps_eligible.avg.per_cycle_active']:
+            if w in h:
+                i = h.index(w)
+                out.append(f"| {w} | {v[i]} | {units[i]} |")
+        sec = None
+        for k in sections:
+            if short_name(k) == short_name(name):
+                sec = sections[k]
+        if sec:
+            hh = sec[0]
+            si, ii, wi = hh.index('Source'), hh.index('Instructions Executed'), hh.index('Warp Stall Sampling (All Samples)')
+            stall_cols = [i for i, n in enumerate(hh) if n.startswith('stall_') and 'Not Issued' not in n]
+            ops, samp, stalls = collections.Counter(), collections.Counter(), collections.Counter()
+            tot = tots = 0.0
+            nsass = 0
+            for r in sec[1:]:
+                if len(r) < len(hh):
+                    continue
+                op = r[si].split()
+                if not op:
+                    continue
+                nsass += 1
+                nm = (op[1] if op[0].startswith('@') else op[0]).split('.')[0]
+                n, s_ = float(r[ii] or 0), float(r[wi] or 0)
+                ops[nm] += n
+                samp[nm] += s_
+                tot += n
+                tots += s_
+                for c in stall_cols:
+                    stalls[hh[c]] += float(r[c] or 0)
+            out += ["", f"SASS instructions in the kernel: {nsass}; warp instructions executed: {tot:.0f}", "",
+                    "| opcode | % of executed | % of stall samples |", "|---|---:|---:|"]
+            for k, n in ops.most_common(14):
+                out.append(f"| {k} | {100 * n / max(tot, 1):.1f} | {100 * samp[k] / max(tots, 1):.1f} |")
+            out += ["", "| stall reason | % of samples |", "|---|---:|"]
+            for k, n in stalls.most_common(8):
+                out.append(f"| {k} | {100 * n / max(tots, 1):.1f} |")
+        open(os.path.join(HERE, f'{tag}_{short_name(name)}.md'), 'w').write('\n'.join(out) + '\n')
+        try:
+            rd = float(v[h.index('dram__bytes_read.sum')]) * UNITS[units[h.index('dram__bytes_read.sum')]]
+            wr = float(v[h.index('dram__bytes_write.sum')]) * UNITS[units[h.index('dram__bytes_write.sum')]]
+            out_traffic[name] = rd + wr
+        except Exception:
+            out_traffic[name] = None
+    return out_traffic
 
 
 if __name__ == '__main__':
     tag = sys.argv[1]
-    launches(tag, sys.argv[2])
-    name, traffic = full(tag, sys.argv[3])
-    print(name, traffic)
+    if sys.argv[2] != '-':
+        launches(tag, sys.argv[2])
+    for name, traffic in full(tag, sys.argv[3]).items():
+        print(traffic, name)
