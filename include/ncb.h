@@ -214,6 +214,20 @@ int ncb_ks_exact_pvalues(ncb_handle *h, int64_t n, const int32_t *n0, const int3
 int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
                int memory, void *stream);
 
+/* --- host-side CSR packer (no GPU work) ---------------------------------------------
+ * Dense per-transcript tensor of the reference's readers (run.py:621-855: data[P][R][V] float32,
+ * NaN = the read does not cover the position) -> the NCB_LAYOUT_CSR arrays.  Two passes so that
+ * many transcripts can be packed into one batch: ncb_pack_count gives the reads per position,
+ * the caller turns the counts of all transcripts into pos_offsets (running sum), ncb_pack_fill
+ * writes signal/label at those offsets (pos_offsets points at this transcript's first
+ * position; the values are offsets into the whole batch).  A read is kept at a position when
+ * its intensity or its dwell is a number; read order is preserved.  `threads` host threads. */
+int ncb_pack_count(const float *data, int64_t n_positions, int32_t n_reads, int32_t n_vars,
+                   int64_t *counts, int threads);
+int ncb_pack_fill(const float *data, const uint8_t *label, int64_t n_positions, int32_t n_reads,
+                  int32_t n_vars, const int64_t *pos_offsets, float *signal_out, uint8_t *label_out,
+                  int threads);
+
 /* --- introspection ---------------------------------------------------------------- */
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */

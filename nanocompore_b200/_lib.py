@@ -44,7 +44,8 @@ NCB_DF_ROWS = 17
 
 EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
-           'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals']
+           'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals',
+           'ncb_pack_count', 'ncb_pack_fill']
 
 
 class NcbOpts(C.Structure):
@@ -115,6 +116,10 @@ def load(path=None):
     lib.ncb_last_timing.restype = C.c_int
     lib.ncb_timing_totals.argtypes = [vp, C.POINTER(i64)] + [C.POINTER(C.c_double)] * 4
     lib.ncb_timing_totals.restype = C.c_int
+    lib.ncb_pack_count.argtypes = [vp, i64, i32, i32, vp, C.c_int]
+    lib.ncb_pack_count.restype = C.c_int
+    lib.ncb_pack_fill.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, C.c_int]
+    lib.ncb_pack_fill.restype = C.c_int
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
     _libs[path] = lib

@@ -141,7 +141,7 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
     const int lo = w.hist[NCB_KS_KIND_SMALL * NCB_KS_BUCKETS];
     const int hi = w.hist[(NCB_KS_KIND_SMALL + 1) * NCB_KS_BUCKETS];
     if (lo + (int)blockIdx.x * KS_SMALL_THREADS >= hi) return;   // whole block idle
-    for (int b = threadIdx.x; b < KS_RECIP_TABLE; b += KS_SMALL_THREADS)
+    for (int b = threadIdx.x; b < KS_RECIP_TABLE + 8; b += KS_SMALL_THREADS)   // + 8: prefetch slack
         rtab[b] = b ? __drcp_rn((double)b) : 0.0;
     __syncthreads();
     const int idx = lo + blockIdx.x * KS_SMALL_THREADS + threadIdx.x;
@@ -167,13 +167,21 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
         const int len = maxj - minj;
         double dj = (double)minj;
         const double *rt = rtab + i + minj;
+        // the cell above and the reciprocal of the next column are fetched before this column's
+        // store (they never alias it: src > jj), so shared-memory latency stays off the
+        // loop-carried chain val -> val
+        double up = (shift < NCB_KS_SMALL_WINDOW) ? AT(shift) : 1.0;
+        double r = rt[0];
         for (int jj = 0; jj < len; ++jj) {
-            const int src = jj + shift;
-            const double up = (src < NCB_KS_SMALL_WINDOW) ? AT(src) : 1.0;
+            const int src = jj + 1 + shift;
+            const double up_next = (src < NCB_KS_SMALL_WINDOW) ? AT(src) : 1.0;
+            const double r_next = rt[jj + 1];
             const double num = NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(val, dj));
-            val = div_by_recip(num, di + dj, rt[jj]);
+            val = div_by_recip(num, di + dj, r);
             AT(jj) = val;
             dj += 1.0;
+            up = up_next;
+            r = r_next;
         }
         curlen = len;
         for (int jj = curlen; jj < lastlen; ++jj) AT(jj) = 1.0;
@@ -263,7 +271,7 @@ static const int KS_HUGE_WARPS = 4, KS_HUGE_BUF = NCB_MAX_READS / 2 + 1;
 int ncb_configure_ks_kernels(void) {
     cudaError_t e;
     e = cudaFuncSetAttribute(ks_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE) * (int)sizeof(double));
+                             (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE + 8) * (int)sizeof(double));
     if (e != cudaSuccess) return -1;
     e = cudaFuncSetAttribute(ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -294,7 +302,7 @@ int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, c
             n0, n1, h, p_out, w, NCB_KS_KIND_LARGE);
     int tblocks = (int)((nprob + KS_SMALL_THREADS - 1) / KS_SMALL_THREADS);
     ks_small_kernel<<<tblocks, KS_SMALL_THREADS,
-                      (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE) * sizeof(double), s>>>(
+                      (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE + 8) * sizeof(double), s>>>(
         n0, n1, h, p_out, w);
     ks_equal_kernel<<<tblocks, KS_SMALL_THREADS, 0, s>>>(n0, h, p_out, w);
     return cudaGetLastError() == cudaSuccess ? 7 : -1;

@@ -73,36 +73,74 @@ class CsrBatch:
         return CsrBatch(self.pos_offsets.pin_memory(), self.signal.pin_memory(), self.label.pin_memory())
 
 
-def pack_csr(transcripts, pin=False):
-    """Packs dense reference tensors into one CSR batch.
+def pack_csr(transcripts, pin=False, threads=None):
+    """Packs dense reference tensors into one CSR batch with libncb's host packer
+    (ncb_pack_count / ncb_pack_fill, multi-threaded C++).
 
-    ``transcripts``: iterable of (data (P,R,2) float32 with NaN, samples (R,), conditions (R,)).
+    ``transcripts``: iterable of (data (P,R,V>=2) float32 with NaN, samples (R,), conditions (R,)).
     A read is kept at a position when any of its two variables is a number.  Read order inside
     a position is the read (column) order of the dense tensor.  Returns (CsrBatch,
     pos_transcript int32 [P_total], pos_index int32 [P_total])."""
-    offs, sigs, labs, ptx, pidx = [np.zeros(1, dtype=np.int64)], [], [], [], []
-    total = 0
-    for ti, (data, samples, conditions) in enumerate(transcripts):
-        data = np.asarray(data, dtype=np.float32)
-        lab = make_labels(samples, conditions)
-        valid = ~np.isnan(data[:, :, :2]).all(2)            # (P, R)
-        counts = valid.sum(1).astype(np.int64)
-        sigs.append(data[:, :, :2][valid])                  # row-major: position, then read
-        labs.append(np.broadcast_to(lab[None, :], valid.shape)[valid])
-        offs.append(total + np.cumsum(counts))
-        total += int(counts.sum())
-        ptx.append(np.full(data.shape[0], ti, dtype=np.int32))
-        pidx.append(np.arange(data.shape[0], dtype=np.int32))
-    sig = np.concatenate(sigs) if sigs else np.zeros((0, 2), np.float32)
-    lab = np.concatenate(labs) if labs else np.zeros((0,), np.uint8)
-    batch = CsrBatch(torch.from_numpy(np.concatenate(offs)),
-                     torch.from_numpy(np.ascontiguousarray(sig.reshape(-1, 2))),
-                     torch.from_numpy(np.ascontiguousarray(lab)))
+    import os
+    lib = L.load()
+    threads = threads or min(16, os.cpu_count() or 1)
+    items = []
+    for data, samples, conditions in transcripts:
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        assert data.ndim == 3 and data.shape[2] >= 2
+        items.append((data, make_labels(samples, conditions)))
+    counts = []
+    for data, lab in items:
+        c = np.empty(data.shape[0], dtype=np.int64)
+        rc = lib.ncb_pack_count(data.ctypes.data, data.shape[0], data.shape[1], data.shape[2],
+                                c.ctypes.data, threads)
+        if rc != L.NCB_OK:
+            raise L.NcbError(rc, "ncb_pack_count")
+        counts.append(c)
+    all_counts = np.concatenate(counts) if counts else np.zeros(0, np.int64)
+    offsets = np.zeros(all_counts.size + 1, dtype=np.int64)
+    np.cumsum(all_counts, out=offsets[1:])
+    E = int(offsets[-1])
+    kw = dict(pin_memory=True) if pin else {}
+    t_off = torch.from_numpy(offsets)
     if pin:
-        batch = batch.pin()
+        t_off = t_off.pin_memory()
+        offsets = t_off.numpy()
+    t_sig = torch.empty((E, 2), dtype=torch.float32, **kw)
+    t_lab = torch.empty((E,), dtype=torch.uint8, **kw)
+    p0 = 0
+    ptx, pidx = [], []
+    for ti, (data, lab) in enumerate(items):
+        P = data.shape[0]
+        rc = lib.ncb_pack_fill(data.ctypes.data, lab.ctypes.data, P, data.shape[1], data.shape[2],
+                               offsets[p0:].ctypes.data, t_sig.data_ptr(), t_lab.data_ptr(), threads)
+        if rc != L.NCB_OK:
+            raise L.NcbError(rc, "ncb_pack_fill")
+        ptx.append(np.full(P, ti, dtype=np.int32))
+        pidx.append(np.arange(P, dtype=np.int32))
+        p0 += P
+    batch = CsrBatch(t_off, t_sig, t_lab)
     return (batch,
             np.concatenate(ptx) if ptx else np.zeros(0, np.int32),
             np.concatenate(pidx) if pidx else np.zeros(0, np.int32))
+
+
+def pack_csr_numpy(transcripts):
+    """Reference packing in numpy (used by the tests to check the native packer)."""
+    offs, sigs, labs = [np.zeros(1, dtype=np.int64)], [], []
+    total = 0
+    for data, samples, conditions in transcripts:
+        data = np.asarray(data, dtype=np.float32)
+        lab = make_labels(samples, conditions)
+        valid = ~np.isnan(data[:, :, :2]).all(2)
+        counts = valid.sum(1).astype(np.int64)
+        sigs.append(data[:, :, :2][valid])
+        labs.append(np.broadcast_to(lab[None, :], valid.shape)[valid])
+        offs.append(total + np.cumsum(counts))
+        total += int(counts.sum())
+    sig = np.concatenate(sigs) if sigs else np.zeros((0, 2), np.float32)
+    lab = np.concatenate(labs) if labs else np.zeros((0,), np.uint8)
+    return np.concatenate(offs), sig.reshape(-1, 2), lab
 
 
 class Results:
