@@ -12,10 +12,11 @@ Workload = BASELINE.json configs[2] ("config 3"): synthetic transcripts of 2,000
 the 126 MB L2, and every step reads a different batch).  K = 20 steps is the whole config.
 
 Printed JSON (one line, rank 0):
-  value     positions/s with the CSR batches already resident in HBM (device timed, CUDA events)
+  value     positions/s with the CSR batches already resident in HBM (device timed, CUDA events),
+            batches issued round-robin on ``--slots`` engines/streams
   e2e       positions/s through the public API with pinned HOST batches: H2D copy of the reads,
-            kernels and D2H copy of the result columns inside the timed region (two engines on
-            two streams so that the copies of one batch overlap the kernels of the other)
+            kernels and D2H copy of the result columns inside the timed region (``--slots`` engines on
+            as many streams so that the copies of one batch overlap the kernels of the others)
   roofline  HBM roofline of the dominant kernel (position kernel), live CUDA-event timing
   cpu_baseline  the oracle port (oracle/comparator.py: numpy + SciPy per position, as the
             reference does) on one host core, on a bounded sample of the same workload
@@ -216,8 +217,9 @@ def run_gpu_arm(args):
     n_batches = K + W
     opts = dict(tests=METHODS, n_samples=4, depleted_condition=0, min_coverage=MIN_COVERAGE,
                 dwell_is_raw=True, cluster_counts='hard')
-    engines = [Engine(local_rank, **opts) for _ in range(2)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    NSLOT = args.slots
+    engines = [Engine(local_rank, **opts) for _ in range(NSLOT)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NSLOT)]
 
     # ---- synthetic batches: pinned host copies (e2e) and device copies (value) ------------
     host_batches, dev_batches = [], []
@@ -252,53 +254,68 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- value: device-resident inputs ------------------------------------------------------
-    eng = engines[0]
-    res_dev = Results(P, 4, dev)
-    tested = torch.zeros((), dtype=torch.int64, device=dev)
+    # ---- value: device-resident inputs, NSLOT engines round-robin on their own streams -------
+    res_dev = [Results(P, 4, dev) for _ in range(NSLOT)]
+    tested_slot = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(NSLOT)]
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    def value_step(b):
-        eng.compare_csr(dev_batches[b], res_dev, wait=False)
-        return ((res_dev.status & L.NCB_POS_DROP_MASK) == 0).sum()
+    def value_step(i, b):
+        s = i % NSLOT
+        with torch.cuda.stream(streams[s]):
+            engines[s].compare_csr(dev_batches[b], res_dev[s], stream=streams[s], wait=False)
+            tested_slot[s] += ((res_dev[s].status & L.NCB_POS_DROP_MASK) == 0).sum()
 
-    for b in range(W):
-        tested += value_step(b)
-    tested.zero_()
-    eng.set_timing(True)
-    launches0 = eng.kernel_launches()
+    for i, b in enumerate(range(W)):
+        value_step(i, b)
+    barrier()
+    for t_ in tested_slot:
+        t_.zero_()
+    launches0 = sum(e.kernel_launches() for e in engines)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for b in range(W, n_batches):
-        tested += value_step(b)
-    ev1.record()
+    main = torch.cuda.current_stream(dev)
+    ev0.record(main)
+    for st in streams:
+        st.wait_event(ev0)
+    for i, b in enumerate(range(W, n_batches)):
+        value_step(i, b)
+    for st in streams:
+        done = torch.cuda.Event()
+        done.record(st)
+        main.wait_event(done)
+    ev1.record(main)
     barrier()
     ms_value = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = eng.kernel_launches() - launches0
-    totals = eng.timing_totals()
-    eng.set_timing(False)
-    tested_positions = int(tested.item())
+    launches = sum(e.kernel_launches() for e in engines) - launches0
+    tested_positions = int(sum(int(t_.item()) for t_ in tested_slot))
     total_tested = sum_over_ranks(float(tested_positions))
     value = total_tested / (ms_value / 1000.0)
 
+    # ---- roofline pass: the same batches on ONE stream, so that every kernel is timed alone --
+    eng = engines[0]
+    eng.set_timing(True)
+    for b in range(W, min(n_batches, W + 6)):
+        eng.compare_csr(dev_batches[b], res_dev[0], wait=False)
+    totals = eng.timing_totals()
+    eng.set_timing(False)
+
     # ---- e2e: pinned host batches through the public API, copies inside the timed region ---
-    res_host = [Results(P, 4, None) for _ in range(2)]
+    res_host = [Results(P, 4, None) for _ in range(NSLOT)]
     for b in range(W):
-        engines[b % 2].compare_csr(host_batches[b], res_host[b % 2], stream=streams[b % 2], wait=False)
+        engines[b % NSLOT].compare_csr(host_batches[b], res_host[b % NSLOT], stream=streams[b % NSLOT], wait=False)
     barrier()
     t0 = time.perf_counter()
     tested_host = 0
-    pending = [None, None]
+    pending = [None] * NSLOT
     for i, b in enumerate(range(W, n_batches)):
-        s = i % 2
+        s = i % NSLOT
         if pending[s] is not None:
             engines[s].wait(streams[s])
             tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
         engines[s].compare_csr(host_batches[b], res_host[s], stream=streams[s], wait=False)
         pending[s] = b
-    for s in range(2):
+    for s in range(NSLOT):
         if pending[s] is not None:
             engines[s].wait(streams[s])
             tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
@@ -359,7 +376,7 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(T), "positions_per_step": P,
                    "tested_positions_per_step": tested_positions / K,
-                   "reads_per_step": entries, "l2": "inputs larger than L2, distinct batch per step",
+                   "reads_per_step": entries, "l2": "inputs larger than L2, distinct batch per step", "slots": NSLOT,
                    "parallelism": f"transcript sharding x{world}, no data-path collective"},
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -383,6 +400,8 @@ def main():
     ap.add_argument('--tx-per-step', type=int, default=50)
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--slots', type=int, default=4,
+                    help="engines/streams of the end-to-end pipeline (copy-in, kernels, copy-out overlap)")
     ap.add_argument('--ref-positions', type=int, default=250,
                     help="positions per slice of the reference arm (one slice per core per step)")
     args = ap.parse_args()
