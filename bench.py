@@ -327,7 +327,20 @@ def run_gpu_arm(args):
     d2h_bytes = res_host[0].nbytes()
     total_launches = int(sum_over_ranks(float(launches)))
 
+    # ---- end-of-run gather of the p-value columns on rank 0 (the only collective of the job;
+    # outside the timed regions: it happens once per run, not per step)
+    gathered = None
     if world > 1:
+        from nanocompore_b200.sharding import gather_columns
+        cols = res_dev[0].pvalues[[L.PV['KS_INTENSITY'], L.PV['KS_DWELL'], L.PV['GMM_CHI2']]].contiguous()
+        keys = (torch.arange(P, device=dev, dtype=torch.int64) | (rank << 32))
+        tg = time.perf_counter()
+        out = gather_columns(cols, keys)
+        torch.cuda.synchronize(dev)
+        if rank == 0:
+            gathered = {"rows": int(out[0].shape[1]), "columns": int(out[0].shape[0]),
+                        "ms": (time.perf_counter() - tg) * 1000.0,
+                        "sorted_by_key": bool((out[1][1:] > out[1][:-1]).all().item())}
         dist.barrier()
     if rank != 0:
         if world > 1:
@@ -383,6 +396,7 @@ def run_gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / K},
         "gpu_launches": total_launches,
+        "final_gather": gathered,
         "clocks": clocks,
         "setup_s": {"generate_and_pack": t_gen},
     }
