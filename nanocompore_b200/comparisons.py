@@ -211,7 +211,8 @@ class TranscriptComparator:
                 results.loc[rows, 'auto_pvalue'] = results.loc[rows, column]
 
     def _combine_context_pvalues(self, results, test):
-        # comparisons.py:436-474 (host side)
+        # comparisons.py:436-474 (host side).  Same arithmetic as the reference's
+        # per-window combine_pvalues_hou, evaluated for all windows of the transcript at once.
         context = self._config.get_sequence_context()
         if self._config.get_sequence_context_weights() == "harmonic":
             weights = harmomic_series(context)
@@ -223,11 +224,7 @@ class TranscriptComparator:
         padded[idx + context] = results[test].to_numpy(dtype=float)
         corr = cross_corr_matrix(padded[context:-context], context)
         windows = np.lib.stride_tricks.sliding_window_view(padded, 2 * context + 1)
-        combined = np.full(windows.shape[0], np.nan)
-        for i, window in enumerate(windows):
-            if not np.isnan(window[context]):
-                combined[i] = combine_pvalues_hou(np.nan_to_num(window, nan=1), weights, corr)
-        return combined[idx]
+        return combine_windows_hou(windows, weights, corr, context)[idx]
 
     def retry(self, fn, delay=5, backoff=5, max_attempts=3, exception=Exception):
         # comparisons.py:608-619; libncb sizes its scratch per batch, so OOM is not expected
@@ -310,6 +307,41 @@ def cross_corr_matrix(pvalues, context=2):
         for y in range(x + 1):
             matrix[x, y] = matrix[y, x] = np.corrcoef(shifted[x], shifted[y])[0, 1]
     return matrix
+
+
+def combine_windows_hou(windows, weights, cor_mat, centre):
+    """``combine_pvalues_hou`` for every row of ``windows`` (n, k) at once: NaN where the centre of
+    the window is NaN, NaNs elsewhere in a window count as 1 (comparisons.py:463-472)."""
+    from scipy.stats import chi2
+    windows = np.asarray(windows, dtype=np.float64)
+    w = np.asarray(weights, dtype=np.float64)
+    k = w.size
+    centre_nan = np.isnan(windows[:, centre])
+    p = np.nan_to_num(windows, nan=1.0)
+    live = ~centre_nan
+    if ((p[live] == 0) | np.isinf(p[live]) | (p[live] > 1)).any():
+        raise ValueError("At least one p-value is invalid")
+    # the scalar sums of combine_pvalues_hou, accumulated in the same order
+    cov_sum = np.float64(0)
+    for i in range(k):
+        for j in range(i + 1, k):
+            r = cor_mat[i][j]
+            cov_sum += w[i] * w[j] * ((3.263 * r) + (0.710 * r ** 2) + (0.027 * r ** 3))
+    sw_sum = np.float64(0)
+    w_sum = np.float64(0)
+    for i in range(k):
+        sw_sum += w[i] ** 2
+        w_sum += w[i]
+    tau = np.zeros(p.shape[0])
+    with np.errstate(divide='ignore'):
+        for i in range(k):
+            tau = tau + w[i] * (-2 * np.log(p[:, i]))
+    scale = (2 * sw_sum + cov_sum) / (2 * w_sum)
+    dof = (4 * w_sum ** 2) / (2 * sw_sum + cov_sum)
+    out = chi2.sf(tau / scale, dof)
+    out = np.where(out == 0, np.finfo(np.float64).tiny, out)
+    out = np.where((p == 1).all(1), 1.0, out)
+    return np.where(centre_nan, np.nan, out)
 
 
 def combine_pvalues_hou(pvalues, weights, cor_mat):
