@@ -198,7 +198,6 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     if (P < 0 || P > 0x7fffffffLL / 2) return fail(h, NCB_ERR_INVALID, "ncb_compare: n_positions out of range");
     if (P == 0) return NCB_OK;
     if (!res->status || !res->pvalues || !res->stats) return fail(h, NCB_ERR_INVALID, "ncb_compare: status, pvalues and stats are required");
-    if (!b->signal || !b->label) return fail(h, NCB_ERR_INVALID, "ncb_compare: null signal or label");
     CK(cudaSetDevice(h->device));
     const ncb_opts &o = h->opts;
     const bool csr = b->layout == NCB_LAYOUT_CSR;
@@ -219,6 +218,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     } else {
         return fail(h, NCB_ERR_INVALID, "ncb_compare: unknown layout");
     }
+    if (E > 0 && (!b->signal || !b->label)) return fail(h, NCB_ERR_INVALID, "ncb_compare: null signal or label");
     const size_t signal_bytes = (size_t)E * n_vars * sizeof(float);
     const int S = o.n_samples;
 
@@ -252,8 +252,8 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     if (b->memory == NCB_MEM_HOST) {
         ENSURE(h->in_signal, signal_bytes);
         ENSURE(h->in_label, label_bytes);
-        CK(cudaMemcpyAsync(h->in_signal.ptr, b->signal, signal_bytes, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(h->in_label.ptr, b->label, label_bytes, cudaMemcpyHostToDevice, s));
+        if (signal_bytes) CK(cudaMemcpyAsync(h->in_signal.ptr, b->signal, signal_bytes, cudaMemcpyHostToDevice, s));
+        if (label_bytes) CK(cudaMemcpyAsync(h->in_label.ptr, b->label, label_bytes, cudaMemcpyHostToDevice, s));
         a.signal = (const float *)h->in_signal.ptr;
         a.label = (const uint8_t *)h->in_label.ptr;
         if (csr) {

@@ -74,8 +74,12 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
             p_out[q] = ncb_nan();
         } else if (hh == 0) {
             p_out[q] = 1.0;
-        } else if (a == b) {
+        } else if (a == b && hh > 0) {
             bin = NCB_KS_KIND_EQUAL * NCB_KS_BUCKETS + cost_bucket((double)a + (double)hh);
+        } else if (min(a, b) > NCB_MAX_READS / 2 || hh < 0) {
+            // outside what ncb_compare can emit (n0 + n1 <= NCB_MAX_READS): the wavefront
+            // kernel's row buffer would not hold the smaller sample
+            p_out[q] = ncb_nan();
         } else {
             KsProblem k = make_problem(a, b, hh);
             long long maxj0 = min(ceildiv_ll(k.h, k.mg), (long long)k.n + 1);

@@ -1,0 +1,105 @@
+"""Edge cases of the C-ABI path on a GPU: empty and degenerate inputs must give the reference's
+answer (NaN / dropped rows), never a fault."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from nanocompore_b200 import _lib as L
+from nanocompore_b200.engine import CsrBatch, make_labels, pack_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def labels(R):
+    return torch.from_numpy(make_labels(np.arange(R) % 4, (np.arange(R) % 4) // 2)).cuda()
+
+
+def test_empty_batches(engine_factory):
+    eng = engine_factory(tests=('GMM', 'KS', 'MW', 'TT'), min_coverage=0)
+    res = eng.compare_dense(torch.zeros((0, 8, 2), device='cuda'), labels(8)).numpy()
+    assert res['status'].size == 0
+    batch, _, _ = pack_csr([])
+    res = eng.compare_csr(batch.to('cuda')).numpy()
+    assert res['status'].size == 0
+    # positions without any read, and a dense tensor without reads at all
+    off = torch.zeros(6, dtype=torch.int64, device='cuda')
+    res = eng.compare_csr(CsrBatch(off, torch.zeros((0, 2), device='cuda'),
+                                   torch.zeros(0, dtype=torch.uint8, device='cuda'))).numpy()
+    assert ((res['status'] & L.NCB_POS_BAD_STD) != 0).all() and np.isnan(res['pvalues']).all()
+    res = eng.compare_dense(torch.zeros((3, 0, 2), device='cuda'), labels(0)).numpy()
+    assert ((res['status'] & L.NCB_POS_DROP_MASK) != 0).all()
+
+
+def test_degenerate_positions(engine_factory):
+    eng = engine_factory(tests=('GMM', 'KS', 'MW', 'TT'), min_coverage=0, with_logit=True)
+    rng = np.random.default_rng(0)
+    R = 40
+    data = rng.standard_normal((8, R, 2)).astype(np.float32)
+    cond = (np.arange(R) % 4) // 2
+    data[0] = np.nan                          # nothing at all
+    data[1, cond == 1] = np.nan               # one condition missing entirely
+    data[2, :, 1] = np.nan                    # dwell missing everywhere
+    data[3, :, 0] = 7.0                       # constant intensity -> std 0
+    data[4, 1:] = np.nan                      # a single read
+    data[5, :, :] = data[5, :1, :]            # all reads identical
+    data[6, 2:] = np.nan                      # two reads, same condition? (reads 0,1 are condition 0)
+    res = eng.compare_dense(torch.from_numpy(data).cuda(), labels(R), diagnostics=True).numpy()
+    st = res['status']
+    for p in (0, 2, 3, 4, 5):
+        assert st[p] & L.NCB_POS_BAD_STD, p
+    assert st[1] == 0 and st[7] == 0
+    # one condition only: the tests have nothing to compare -> NaN p-values, no fault;
+    # the mixture fit itself is defined (all reads of condition 0)
+    for row in ('KS_INTENSITY', 'KS_DWELL', 'MW_INTENSITY', 'TT_DWELL'):
+        assert np.isnan(res['pvalues'][L.PV[row]][1])
+    assert np.isfinite(res['diag_f64'][L.DF['BIC1']][1])
+    assert (res['counts'][2:, :, 1] == 0).all()          # samples of condition 1 saw no read
+    # position 6: two reads of one condition
+    assert st[6] == 0 or st[6] & L.NCB_POS_BAD_STD
+    ok = res['pvalues'][:, 7]
+    assert np.isfinite(ok[L.PV['KS_INTENSITY']]) and np.isfinite(ok[L.PV['TT_DWELL']])
+
+
+def test_min_coverage_above_everything(engine_factory):
+    eng = engine_factory(tests=('KS',), min_coverage=1000)
+    data = np.random.default_rng(1).standard_normal((5, 30, 2)).astype(np.float32)
+    res = eng.compare_dense(torch.from_numpy(data).cuda(), labels(30)).numpy()
+    assert (res['status'] == L.NCB_POS_LOW_COVERAGE).all() and np.isnan(res['pvalues']).all()
+
+
+def test_invalid_arguments_return_errors(engine_factory):
+    eng = engine_factory(tests=('KS',))
+    lib = eng.lib
+    b, r = L.NcbBatch(), L.NcbResults()
+    b.layout, b.memory, b.n_positions = 7, L.NCB_MEM_DEVICE, 4
+    assert lib.ncb_compare(eng._handle, C.byref(b), C.byref(r), None) == L.NCB_ERR_INVALID
+    assert b"required" in lib.ncb_last_error(eng._handle) or b"layout" in lib.ncb_last_error(eng._handle)
+    o = L.default_opts()
+    o.n_samples = 1000
+    assert lib.ncb_set_opts(eng._handle, C.byref(o)) == L.NCB_ERR_INVALID
+    with pytest.raises(L.NcbError):
+        eng.configure(n_samples=1000)
+    assert eng.ks_exact_pvalues([], [], []).size == 0
+    assert eng.bh_fdr(np.zeros(0)).size == 0
+    assert np.isnan(eng.bh_fdr(np.array([np.nan, np.nan]))).all()
+
+
+def test_many_samples_and_unknown_sample_ids(engine_factory):
+    """Sample ids beyond n_samples are ignored in the counts (the reference only reports the
+    configured samples); 64 samples are supported."""
+    eng = engine_factory(tests=('GMM',), min_coverage=0, n_samples=64)
+    rng = np.random.default_rng(3)
+    R = 256
+    data = rng.standard_normal((4, R, 2)).astype(np.float32)
+    data[:, R // 2:, :] += 3
+    samples = np.arange(R) % 64
+    cond = (np.arange(R) >= R // 2).astype(int)
+    lab = torch.from_numpy(make_labels(samples, cond)).cuda()
+    res = eng.compare_dense(torch.from_numpy(data).cuda(), lab, diagnostics=True).numpy()
+    tot = (res['counts'][:, 0] + res['counts'][:, 1])
+    assert (tot.sum(0) == res['diag_i64'][L.DI['N_GMM']]).all()
+    eng4 = engine_factory(tests=('GMM',), min_coverage=0, n_samples=4)
+    res4 = eng4.compare_dense(torch.from_numpy(data).cuda(), lab).numpy()
+    assert (res4['counts'][:4] == res['counts'][:4]).all()
