@@ -109,10 +109,11 @@ typedef struct {
     int64_t n_positions;        /* P                                                     */
     int64_t n_entries;          /* CSR: E = pos_offsets[P]; dense: P*R                   */
     const int64_t *pos_offsets; /* CSR: [P+1]; dense: NULL                               */
-    const float *signal;        /* CSR: [E][2] {intensity, dwell}; dense: [P][R][V]      */
+    const float *signal;        /* CSR: [E][V] {intensity, dwell[, motor dwell]}; dense: [P][R][V] */
     const uint8_t *label;       /* CSR: [E]; dense: [R]                                  */
     int32_t n_reads;            /* dense: R                                              */
-    int32_t n_vars;             /* dense: V (2, or 3 with the motor-dwell column)        */
+    int32_t n_vars;             /* V: 2, or 3 with the motor-dwell column of
+                                   Worker._prepare_data (run.py:575-584); CSR: 0 means 2  */
 } ncb_batch;
 
 /* rows of ncb_results.pvalues ([NCB_PV_ROWS][P], float64, NaN = not tested) */
@@ -135,7 +136,11 @@ enum {
     NCB_ST_C2_MEDIAN_INTENSITY = 8, NCB_ST_C2_MEDIAN_DWELL = 9,
     NCB_ST_C2_SD_INTENSITY = 10, NCB_ST_C2_SD_DWELL = 11,
     NCB_ST_GMM_LOR = 12,
-    NCB_ST_ROWS = 13
+    /* motor-dwell shift statistics, written only for 3-variable batches (motor_dwell_offset > 0,
+     * comparisons.py:411-433): c1/c2 x mean/median/sd of the third variable */
+    NCB_ST_C1_MEAN_MOTOR = 13, NCB_ST_C1_MEDIAN_MOTOR = 14, NCB_ST_C1_SD_MOTOR = 15,
+    NCB_ST_C2_MEAN_MOTOR = 16, NCB_ST_C2_MEDIAN_MOTOR = 17, NCB_ST_C2_SD_MOTOR = 18,
+    NCB_ST_ROWS = 19
 };
 
 /* rows of ncb_results.diag_i64 ([NCB_DI_ROWS][P]) -- exact integer statistics */

@@ -31,8 +31,10 @@ PV = dict(KS_INTENSITY=0, KS_DWELL=1, MW_INTENSITY=2, MW_DWELL=3, TT_INTENSITY=4
 NCB_PV_ROWS = 9
 ST = dict(C1_MEAN_INTENSITY=0, C1_MEAN_DWELL=1, C1_MEDIAN_INTENSITY=2, C1_MEDIAN_DWELL=3,
           C1_SD_INTENSITY=4, C1_SD_DWELL=5, C2_MEAN_INTENSITY=6, C2_MEAN_DWELL=7,
-          C2_MEDIAN_INTENSITY=8, C2_MEDIAN_DWELL=9, C2_SD_INTENSITY=10, C2_SD_DWELL=11, GMM_LOR=12)
-NCB_ST_ROWS = 13
+          C2_MEDIAN_INTENSITY=8, C2_MEDIAN_DWELL=9, C2_SD_INTENSITY=10, C2_SD_DWELL=11, GMM_LOR=12,
+          C1_MEAN_MOTOR=13, C1_MEDIAN_MOTOR=14, C1_SD_MOTOR=15, C2_MEAN_MOTOR=16, C2_MEDIAN_MOTOR=17,
+          C2_SD_MOTOR=18)
+NCB_ST_ROWS = 19
 DI = dict(N0_INTENSITY=0, N1_INTENSITY=1, N0_DWELL=2, N1_DWELL=3, KS_H_INTENSITY=4, KS_H_DWELL=5,
           MW_U2_INTENSITY=6, MW_U2_DWELL=7, MW_TIE_INTENSITY=8, MW_TIE_DWELL=9,
           CONT_00=10, CONT_01=11, CONT_10=12, CONT_11=13, EM_ITERS=14, N_GMM=15, N_OUTLIERS=16)

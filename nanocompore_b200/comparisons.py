@@ -18,8 +18,10 @@ outlier filter, standardisation, KS / MW / TT, both Gaussian mixtures, contingen
 LOR, chi-squared) and this module only assembles the DataFrame.  There is no CPU fallback:
 with no GPU or no libncb.so the constructor's first use raises.
 
-Not supported (raises NotImplementedError): ``motor_dwell_offset > 0`` (3-variable GMM,
-SURVEY 8f N4) and the ``GOF`` test (out of scope).
+``motor_dwell_offset > 0`` (a third variable, comparisons.py:285-335) is supported: positions
+where at least 90 % of the reads carry a motor dwell are fitted in 3 variables, the others in 2,
+inside the same libncb call.  Not supported (raises NotImplementedError): the ``GOF`` test
+(out of scope).
 """
 import numpy as np
 import pandas as pd
@@ -35,8 +37,14 @@ MOTOR = 2
 HARD_ASSIGNMENT = 'hard'
 SOFT_ASSIGNMENT = 'soft'
 
-SHIFT_COLUMNS = [(f"c{c + 1}_{stat}_{dim}", L.ST[f"C{c + 1}_{stat.upper()}_{dim.upper()}"])
-                 for c in (0, 1) for stat in ('mean', 'median', 'sd') for dim in ('intensity', 'dwell')]
+def shift_columns(with_motor):
+    """Column name -> stats row, in the reference's insertion order (comparisons.py:421-433)."""
+    dims = [('intensity', 'INTENSITY'), ('dwell', 'DWELL')] + ([('motor_dwell', 'MOTOR')] if with_motor else [])
+    return [(f"c{c + 1}_{stat}_{dim}", L.ST[f"C{c + 1}_{stat.upper()}_{key}"])
+            for c in (0, 1) for stat in ('mean', 'median', 'sd') for dim, key in dims]
+
+
+SHIFT_COLUMNS = shift_columns(False)
 
 _NONPARAMETRIC = {'KS': ('KS_INTENSITY', 'KS_DWELL'), 'MW': ('MW_INTENSITY', 'MW_DWELL'),
                   'TT': ('TT_INTENSITY', 'TT_DWELL')}
@@ -104,9 +112,10 @@ class TranscriptComparator:
         n_positions = len(positions)
         if n_positions == 0:
             return (transcript, None)
-        if self._motor_dwell_offset > 0 or data.shape[2] != 2:
-            raise NotImplementedError(
-                "motor_dwell_offset > 0 (3-variable GMM) is not implemented in nanocompore_b200")
+        with_motor = self._motor_dwell_offset > 0
+        if data.shape[2] != (3 if with_motor else 2):
+            raise NanocomporeError(
+                f"data has {data.shape[2]} variables, motor_dwell_offset = {self._motor_dwell_offset}")
 
         engine = self._engine(device)
         pos_host = positions.cpu() if isinstance(positions, torch.Tensor) else torch.as_tensor(positions)
@@ -122,7 +131,7 @@ class TranscriptComparator:
                 f"A position of transcript {transcript.name} has more than {L.NCB_MAX_READS} reads; "
                 "lower downsample_high_coverage")
 
-        for column, row in SHIFT_COLUMNS:
+        for column, row in shift_columns(with_motor):
             results[column] = st[row]
 
         # comparisons.py:108-120

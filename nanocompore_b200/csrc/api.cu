@@ -26,7 +26,7 @@ struct ncb_handle {
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
-    DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n;
+    DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n, zbuf3, gmm_n3;
     DevBuf wl_count, wl_list;
     DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch;
     DevBuf fdr_scratch, fdr_p, fdr_q;
@@ -166,7 +166,7 @@ void ncb_destroy(ncb_handle *h) {
     cudaSetDevice(h->device);
     DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
                      &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
-                     &h->ks_h, &h->zbuf, &h->gmm_n, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
+                     &h->ks_h, &h->zbuf, &h->gmm_n, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
                      &h->kw_bin, &h->kw_fetch, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d};
     for (DevBuf *b : all) release(*b);
@@ -209,7 +209,8 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
         E = b->n_entries;
         if (E < 0) return fail(h, NCB_ERR_INVALID, "ncb_compare: negative n_entries");
         label_bytes = (size_t)E;
-        n_vars = 2;
+        n_vars = b->n_vars == 0 ? 2 : b->n_vars;
+        if (n_vars < 2 || n_vars > 3) return fail(h, NCB_ERR_INVALID, "ncb_compare: n_vars must be 2 or 3");
     } else if (b->layout == NCB_LAYOUT_DENSE) {
         if (b->n_reads < 0 || b->n_vars < 2 || b->n_vars > 3) return fail(h, NCB_ERR_INVALID, "ncb_compare: dense batch needs n_reads >= 0 and 2 <= n_vars <= 3");
         E = P * (int64_t)b->n_reads;
@@ -310,6 +311,12 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
         ENSURE(h->gmm_n, (size_t)P * sizeof(int32_t));
         a.zbuf = (float2 *)h->zbuf.ptr;
         a.gmm_n = (int32_t *)h->gmm_n.ptr;
+        if (n_vars == 3) {
+            ENSURE(h->zbuf3, (size_t)E * sizeof(float));
+            ENSURE(h->gmm_n3, (size_t)P * sizeof(int32_t));
+            a.zbuf3 = (float *)h->zbuf3.ptr;
+            a.gmm_n3 = (int32_t *)h->gmm_n3.ptr;
+        }
     }
     ENSURE(h->wl_count, NCB_NUM_CLASSES * sizeof(int32_t));
     ENSURE(h->wl_list, (size_t)P * NCB_NUM_CLASSES * sizeof(int32_t));

@@ -32,7 +32,9 @@ struct NcbDeviceArgs {
     double *diag_f64;
     // scratch: hand-over from the statistics kernel to the mixture kernel
     float2 *zbuf;                // standardised (intensity, dwell) per entry, NaN x = not in the fit
-    int32_t *gmm_n;              // [P] reads in the fit, 0 = no mixture test on this position
+    int32_t *gmm_n;              // [P] reads in the 2-variable fit, 0 = none on this position
+    float *zbuf3;                // 3-variable batches: standardised motor dwell per entry
+    int32_t *gmm_n3;             // 3-variable batches: [P] reads in the 3-variable fit, 0 = none
     // scratch: exact-KS work items, one per (variable, position): index v * P + p
     int32_t *ks_n0;
     int32_t *ks_n1;

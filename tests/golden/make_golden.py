@@ -135,11 +135,15 @@ def synthetic(ref):
     out = {}
     cases = [dict(seed=1, P=60, n=40, quantised=False), dict(seed=2, P=60, n=40, quantised=True),
              dict(seed=3, P=40, n=90, quantised=False), dict(seed=4, P=80, n=8, quantised=True,
-                                                             gap_rate=0.1)]
+                                                             gap_rate=0.1),
+             # motor_dwell_offset > 0: third variable, 2- and 3-variable mixtures
+             dict(seed=5, P=70, n=40, quantised=False, motor=6, gap_rate=0.08),
+             dict(seed=6, P=50, n=30, quantised=True, motor=3, gap_rate=0.02)]
     for ci, case in enumerate(cases):
-        kw = {k: v for k, v in case.items() if k not in ('seed', 'P', 'n')}
+        kw = {k: v for k, v in case.items() if k not in ('seed', 'P', 'n', 'motor')}
         tx = make_transcript(np.random.default_rng(case['seed']), case['P'], case['n'], **kw)
-        conf = reference_config(ref, comparison_methods=['GMM', 'KS', 'MW', 'TT'], min_coverage=1)
+        conf = reference_config(ref, comparison_methods=['GMM', 'KS', 'MW', 'TT'], min_coverage=1,
+                                motor_dwell_offset=case.get('motor', 0))
 
         class FakeWorker:
             _conf = conf
@@ -154,6 +158,7 @@ def synthetic(ref):
         comparator = ref.comparisons.TranscriptComparator(config=conf, worker=worker)
         _, df = comparator.compare_transcript(Transcript(ci, f'syn{ci}', 'A' * case['P']),
                                               tensor.clone(), s_t, c_t, pos_t, 'cpu')
+        out[f'case{ci}/motor_dwell_offset'] = np.array(case.get('motor', 0))
         out[f'case{ci}/raw'] = raw
         out[f'case{ci}/prepared'] = tensor.numpy()
         out[f'case{ci}/prepared_positions'] = pos_t.numpy()

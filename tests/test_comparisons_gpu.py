@@ -14,7 +14,7 @@ import torch
 from nanocompore_b200.comparisons import TranscriptComparator
 from nanocompore_b200.config import PathConfig
 from oracle import prep as oprep
-from test_oracle_vs_reference import SHIFT, load, result_frame
+from test_oracle_vs_reference import SHIFT, SHIFT_MOTOR, load, result_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -48,7 +48,7 @@ def compare(cfg, data, samples, conditions, positions, worker=None, **kw):
 def check_against_reference(df, ref, methods, labels):
     assert len(df) == len(ref['pos'])
     np.testing.assert_array_equal(df['pos'].to_numpy(), ref['pos'])
-    for col in SHIFT:
+    for col in SHIFT + [c for c in SHIFT_MOTOR if c in ref]:
         np.testing.assert_allclose(df[col].to_numpy(), ref[col], rtol=2e-6, atol=1e-6, equal_nan=True, err_msg=col)
     for t in ('KS', 'MW', 'TT'):
         if t in methods:
@@ -88,13 +88,16 @@ def test_fixture_config1_rows_and_values():
     assert rows == 3519
 
 
-@pytest.mark.parametrize('case', range(4))
+@pytest.mark.parametrize('case', range(6))
 def test_synthetic_against_reference(case):
+    """cases 4, 5: motor_dwell_offset > 0 -- 18 shift statistics, 2- and 3-variable mixtures."""
     z = load('synthetic_ref.npz')
     ref = result_frame(z, f'case{case}/result')
     methods = ['GMM', 'KS', 'MW', 'TT']
-    df = compare(config(comparison_methods=methods), z[f'case{case}/prepared'], z[f'case{case}/samples'],
-                 z[f'case{case}/conditions'], z[f'case{case}/prepared_positions'])
+    motor = int(z[f'case{case}/motor_dwell_offset'])
+    df = compare(config(comparison_methods=methods, motor_dwell_offset=motor), z[f'case{case}/prepared'],
+                 z[f'case{case}/samples'], z[f'case{case}/conditions'], z[f'case{case}/prepared_positions'])
+    assert ('c2_sd_motor_dwell' in df.columns) == (motor > 0)
     check_against_reference(df, ref, methods, ['kd1', 'kd2', 'wt1', 'wt2'])
 
 
@@ -170,9 +173,6 @@ def test_sequence_context_columns_match_the_oracle():
 
 
 def test_unsupported_options_raise():
-    with pytest.raises(NotImplementedError):
-        compare(config(motor_dwell_offset=3), np.zeros((2, 8, 3), np.float32), np.zeros(8), np.zeros(8),
-                np.arange(2, dtype=np.int16))
     with pytest.raises(NotImplementedError):
         compare(config(comparison_methods=['GOF']), np.zeros((2, 8, 2), np.float32), np.zeros(8), np.zeros(8),
                 np.arange(2, dtype=np.int16))

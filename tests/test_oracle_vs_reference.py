@@ -33,10 +33,13 @@ def result_frame(z, prefix):
     return {c: z[f'{prefix}/{c}'] for c in cols}
 
 
+SHIFT_MOTOR = [f"c{c}_{s}_motor_dwell" for c in (1, 2) for s in ('mean', 'median', 'sd')]
+
+
 def check_frame(df, ref, methods, sample_labels):
     assert len(df) == len(ref['pos'])
     np.testing.assert_array_equal(df['pos'].to_numpy(), ref['pos'])
-    for col in SHIFT:
+    for col in SHIFT + [c for c in SHIFT_MOTOR if c in ref]:
         np.testing.assert_allclose(df[col].to_numpy(), ref[col], rtol=2e-6, atol=1e-6, equal_nan=True,
                                    err_msg=col)
     for t in ('KS', 'MW', 'TT'):
@@ -66,12 +69,15 @@ def test_reference_own_tests_pass_with_restated_gmm():
     assert rec['returncode'] == 0 and '14 passed' in rec['summary'], rec
 
 
-@pytest.mark.parametrize('case', range(4))
+@pytest.mark.parametrize('case', range(6))
 def test_synthetic_cases(case):
+    """cases 4 and 5 have motor_dwell_offset > 0 (third variable; 2- and 3-variable mixtures)."""
     z = load('synthetic_ref.npz')
     ref = result_frame(z, f'case{case}/result')
     methods = ['GMM', 'KS', 'MW', 'TT']
-    cmp_ = OracleComparator(OracleConfig(comparison_methods=methods))
+    motor = int(z[f'case{case}/motor_dwell_offset'])
+    assert ('c1_mean_motor_dwell' in ref) == (motor > 0)
+    cmp_ = OracleComparator(OracleConfig(comparison_methods=methods, motor_dwell_offset=motor))
     df = cmp_.compare_transcript(case, z[f'case{case}/prepared'], z[f'case{case}/samples'],
                                  z[f'case{case}/conditions'], z[f'case{case}/prepared_positions'])
     check_frame(df, ref, methods, ['kd1', 'kd2', 'wt1', 'wt2'])
@@ -81,18 +87,20 @@ def test_prepare_data_matches_reference():
     """run.py:532-601 incl. the float32 log10 (the oracle's convention is fp64 log10 rounded
     once; numpy's float32 log10 may differ in the last bit)."""
     z = load('synthetic_ref.npz')
-    for case in range(4):
+    for case in range(6):
         data, samples, conditions, positions = oprep.prepare_data(
-            z[f'case{case}/raw'], z[f'case{case}/samples'], z[f'case{case}/conditions'])
+            z[f'case{case}/raw'], z[f'case{case}/samples'], z[f'case{case}/conditions'],
+            int(z[f'case{case}/motor_dwell_offset']))
         data, positions = oprep.filter_low_cov_positions(data, positions, conditions, 1)
         np.testing.assert_array_equal(positions, z[f'case{case}/prepared_positions'])
         want = z[f'case{case}/prepared']
         np.testing.assert_array_equal(data[:, :, 0], want[:, :, 0])
         # libm's float32 log10 is not correctly rounded (only ~40 % of the values are bit-equal to
         # the correctly rounded ones here); the two never differ by more than 2 float32 ulps
-        ok = ~np.isnan(want[:, :, 1])
-        ulps = np.abs(data[:, :, 1][ok].view(np.int32).astype(np.int64) -
-                      want[:, :, 1][ok].view(np.int32).astype(np.int64))
+        ok = ~np.isnan(want[:, :, 1:])
+        assert (np.isnan(data[:, :, 1:]) == ~ok).all()
+        ulps = np.abs(data[:, :, 1:][ok].view(np.int32).astype(np.int64) -
+                      want[:, :, 1:][ok].view(np.int32).astype(np.int64))
         assert ulps.max() <= 2
 
 

@@ -10,19 +10,20 @@ from test_oracle_vs_reference import load
 
 def test_prepare_and_filter_match_the_reference_goldens():
     z = load('synthetic_ref.npz')
-    for case in range(4):
+    for case in range(6):
+        motor = int(z[f'case{case}/motor_dwell_offset'])
         t, s, c, pos = prep.prepare_data(z[f'case{case}/raw'].copy(), z[f'case{case}/samples'],
-                                         z[f'case{case}/conditions'])
+                                         z[f'case{case}/conditions'], motor)
         t, pos = prep.filter_low_cov_positions(t, pos, c, 1)
         assert t.dtype == torch.float32 and s.dtype == torch.int16 and pos.dtype == torch.int16
         np.testing.assert_array_equal(pos.numpy(), z[f'case{case}/prepared_positions'])
         want = z[f'case{case}/prepared']
         np.testing.assert_array_equal(t.numpy()[:, :, 0], want[:, :, 0])
-        ok = ~np.isnan(want[:, :, 1])
-        ulps = np.abs(t.numpy()[:, :, 1][ok].view(np.int32).astype(np.int64) - want[:, :, 1][ok].view(np.int32).astype(np.int64))
+        ok = ~np.isnan(want[:, :, 1:])
+        ulps = np.abs(t.numpy()[:, :, 1:][ok].view(np.int32).astype(np.int64) - want[:, :, 1:][ok].view(np.int32).astype(np.int64))
         assert ulps.max() <= 2            # libm's float32 log10 vs the correctly rounded one
         # and bit-equal to the oracle's convention
-        od, _, _, opos = oprep.prepare_data(z[f'case{case}/raw'], z[f'case{case}/samples'], z[f'case{case}/conditions'])
+        od, _, _, opos = oprep.prepare_data(z[f'case{case}/raw'], z[f'case{case}/samples'], z[f'case{case}/conditions'], motor)
         od, opos = oprep.filter_low_cov_positions(od, opos, z[f'case{case}/conditions'], 1)
         assert np.array_equal(t.numpy(), od, equal_nan=True)
 
