@@ -12,7 +12,7 @@ namespace ncb {
 typedef unsigned long long u64;
 
 #define NCB_FULL 0xffffffffu
-#define NCB_RED_MAX 16   /* most 64-bit values reduced in one call */
+#define NCB_RED_MAX 13   /* most 64-bit values reduced in one call */
 #define NCB_RED_STRIDE 13 /* row stride of a warp group's reduction scratch (odd: no bank conflicts);
                              warp groups reduce at most 13 values at once */
 #define NCB_RED_WARP_WORDS (32 * NCB_RED_STRIDE + 16)   /* 64-bit words of scratch per warp group */

@@ -249,7 +249,7 @@ def test_motor_dwell_three_variables(engine_factory, n, gap):
     # both kinds of position occur
     valid = ~np.isnan(std_data[ok])
     use3 = (valid[:, :, 0] & valid[:, :, 2]).sum(1) >= 0.9 * valid[:, :, 0].sum(1)
-    assert use3.any() and (~use3).any()
+    assert use3.any() and ((~use3).any() or gap < 0.05)    # the gappy case has both kinds
     assert_pvalues_close(res['pvalues'][L.PV['GMM_CHI2']][ok], df['GMM_chi2_pvalue'].to_numpy(), 'GMM chi2 p')
     assert_equal_nan(res['stats'][L.ST['GMM_LOR']][ok], df['GMM_LOR'].to_numpy(dtype=np.float32), 'LOR')
     for label, sid in SAMPLE_IDS.items():
