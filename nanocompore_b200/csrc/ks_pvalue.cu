@@ -82,12 +82,25 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
             p_out[q] = ncb_nan();
         } else {
             KsProblem k = make_problem(a, b, hh);
-            long long maxj0 = min(ceildiv_ll(k.h, k.mg), (long long)k.n + 1);
-            long long lenA = min(2 * maxj0 + 2, (long long)k.n + 1);
-            double width = fmin(2.0 * (double)k.h / (double)k.mg + 1.0, (double)k.n + 1.0);
-            int kind = (lenA <= NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) ? NCB_KS_KIND_SMALL
-                       : (k.n <= NCB_KS_LARGE_MAXN ? NCB_KS_KIND_LARGE : NCB_KS_KIND_HUGE);
-            bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
+            const double lcm = (double)k.mg * (double)k.n;
+            const double d = (double)hh / lcm;
+            // P(D >= d) is of the order of exp(-2 d^2 mn/(m+n)); beyond exp(-921) = 1e-400 the
+            // lattice recurrence underflows to exactly 0 (smallest denormal 4.9e-324, 76 orders
+            // of magnitude of margin), which is also what SciPy returns: skip the walk.
+            if (2.0 * d * d * (double)k.m * (double)k.n / (double)(k.m + k.n) > 921.0) {
+                p_out[q] = 0.0;
+            } else {
+                long long maxj0 = min(ceildiv_ll(k.h, k.mg), (long long)k.n + 1);
+                long long lenA = min(2 * maxj0 + 2, (long long)k.n + 1);
+                double width = fmin(2.0 * (double)k.h / (double)k.mg + 1.0, (double)k.n + 1.0);
+                // columns a 32-row chunk of the wavefront touches, plus those entering next
+                double span = width + 2.0 * (32.0 * (double)k.ng / (double)k.mg) + 8.0;
+                int kind;
+                if (lenA <= NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) kind = NCB_KS_KIND_SMALL;
+                else if (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL) kind = NCB_KS_KIND_LARGE;
+                else kind = NCB_KS_KIND_HUGE;
+                bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
+            }
         }
         w.bin[q] = (uint8_t)bin;
         if (bin != 255) atomicAdd(&w.hist[bin], 1);
@@ -206,13 +219,20 @@ __global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_o
 }
 
 // ---- warp per problem: skewed wavefront over 32 rows --------------------------------------
-template <int WARPS, int ROWBUF>
+// The row above the current 32-row chunk lives in a power-of-two ring of RING doubles indexed
+// by j & (RING - 1).  The band moves to the right, so a slot is reused only by columns RING
+// apart; classification guarantees RING >= the widest span a chunk touches (or RING > n, in
+// which case the ring never wraps).  Slots that enter the band for the first time must read 1
+// ("outside the band"): they are reset at the end of the chunk before.
+template <int WARPS, int RING, bool WRAP>
 __global__ void __launch_bounds__(WARPS * 32)
 ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out,
                NcbKsWork w, int kind) {
-    extern __shared__ double rows_all[];   // [WARPS][ROWBUF]
+    extern __shared__ double rows_all[];   // [WARPS][RING]
     const int lane = threadIdx.x & 31;
-    double *prev = rows_all + (size_t)(threadIdx.x >> 5) * ROWBUF;
+    double *prev = rows_all + (size_t)(threadIdx.x >> 5) * RING;
+    constexpr int MASK = WRAP ? RING - 1 : -1;   // WRAP = false: RING > n, plain indexing
+    static_assert(!WRAP || (RING & (RING - 1)) == 0, "ring size must be a power of two");
     const int lo = w.hist[kind * NCB_KS_BUCKETS];
     const int hi = w.hist[(kind + 1) * NCB_KS_BUCKETS];
     for (;;) {
@@ -222,45 +242,56 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
         if (idx >= hi) break;
         const int q = w.list[idx];
         const KsProblem k = make_problem(n0[q], n1[q], h[q]);
+        // every quantity below fits in 32 bits: n0 + n1 <= NCB_MAX_READS, so ng*i, mg*j and
+        // h <= lcm are at most 5120 * 5120
         const int n = k.n, m = k.m;
-        const long long mg = k.mg, ng = k.ng, hh = k.h;
-        const long long maxj0 = min(ceildiv_ll(hh, mg), (long long)n + 1);
-        for (int j = lane; j <= n; j += 32) prev[j] = (j < maxj0) ? 0.0 : 1.0;
+        const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
+        const int maxj0 = min((hh + mg - 1) / mg, n + 1);
+        const int fill = min(n + 1, RING);
+        for (int j = lane; j < fill; j += 32) prev[j] = (j < maxj0) ? 0.0 : 1.0;
         __syncwarp();
+        int jhi_done = min(n + 1, RING);          // columns below this hold valid ring slots
         for (int i0 = 1; i0 <= m; i0 += 32) {
             const int rows = min(32, m - i0 + 1);
             const int ilast = i0 + rows - 1;
-            long long jlo_l = max(floordiv_ll(ng * i0 - hh, mg) + 1, 0LL);
-            const int jlo = (int)min(jlo_l, (long long)n);
-            const int jhi = (int)min(ceildiv_ll(ng * ilast + hh, mg), (long long)n + 1);
+            const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
+            const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);
+            const int jhi = min((ng * ilast + hh + mg - 1) / mg, n + 1);
+            // slots entering the band in this chunk that were last used RING columns ago
+            for (int j = jhi_done + lane; j < jhi; j += 32) prev[j & MASK] = 1.0;
+            jhi_done = max(jhi_done, jhi);
+            __syncwarp();
             const int i = i0 + lane;
             const bool row_on = lane < rows;
             const double di = (double)i;
-            const long long ngi = ng * i;
+            const int ngi = ng * i;
             double left = 1.0, cur = 1.0;
             const int nsteps = (jhi - jlo) + rows - 1;
+            int j = jlo - lane;
+            double dj = (double)j;
+            double den = (double)(i0 + jlo);
+#pragma unroll 1
             for (int t = 0; t < nsteps; ++t) {
-                const int j = jlo + t - lane;
                 // i + j = i0 + jlo + t on every lane: one reciprocal per step for the warp
-                const double den = (double)(i0 + jlo + t);
                 const double rden = __drcp_rn(den);
                 const double up_sh = __shfl_up_sync(0xffffffffu, cur, 1);
-                const bool act = row_on && j >= jlo && j < jhi;
-                if (act) {
-                    const double up = (lane == 0) ? prev[j] : up_sh;
-                    const long long v = ngi - mg * j;
+                if (row_on && j >= jlo && j < jhi) {
+                    const double up = (lane == 0) ? prev[j & MASK] : up_sh;
+                    const int v = ngi - mg * j;
                     double val = 1.0;
-                    if ((v < 0 ? -v : v) < hh)
-                        val = div_by_recip(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, (double)j)),
-                                           den, rden);
+                    if (abs(v) < hh)
+                        val = div_by_recip(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, dj)), den, rden);
                     cur = val;
                     left = val;
-                    if (lane == rows - 1) prev[j] = val;
+                    if (lane == rows - 1) prev[j & MASK] = val;
                 }
+                ++j;
+                dj += 1.0;
+                den += 1.0;
             }
             __syncwarp();
         }
-        if (lane == 0) p_out[q] = clip01(prev[n]);
+        if (lane == 0) p_out[q] = clip01(prev[n & MASK]);
         __syncwarp();
     }
 }
@@ -269,19 +300,19 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
 
 using namespace ncb;
 
-static const int KS_LARGE_WARPS = 8, KS_LARGE_BUF = NCB_KS_LARGE_MAXN + 1;
-static const int KS_HUGE_WARPS = 4, KS_HUGE_BUF = NCB_MAX_READS / 2 + 1;
+static const int KS_LARGE_WARPS = 8, KS_LARGE_BUF = NCB_KS_RING_SMALL;
+static const int KS_HUGE_WARPS = 5, KS_HUGE_BUF = NCB_KS_RING_FULL;
 
 int ncb_configure_ks_kernels(void) {
     cudaError_t e;
     e = cudaFuncSetAttribute(ks_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE + 8) * (int)sizeof(double));
     if (e != cudaSuccess) return -1;
-    e = cudaFuncSetAttribute(ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF>,
+    e = cudaFuncSetAttribute(ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                              KS_LARGE_WARPS * KS_LARGE_BUF * (int)sizeof(double));
     if (e != cudaSuccess) return -1;
-    e = cudaFuncSetAttribute(ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF>,
+    e = cudaFuncSetAttribute(ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                              KS_HUGE_WARPS * KS_HUGE_BUF * (int)sizeof(double));
     if (e != cudaSuccess) return -1;
@@ -298,10 +329,10 @@ int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, c
     ks_scan_kernel<<<1, NCB_KS_NBINS, 0, s>>>(w);
     ks_scatter_kernel<<<blocks, 256, 0, s>>>(nprob, w);
     // the long problems first: their warps are busy while the short kernels fill the rest
-    ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF>
+    ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF, false>
         <<<sm_count, KS_HUGE_WARPS * 32, KS_HUGE_WARPS * KS_HUGE_BUF * sizeof(double), s>>>(
             n0, n1, h, p_out, w, NCB_KS_KIND_HUGE);
-    ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF>
+    ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF, true>
         <<<sm_count * 3, KS_LARGE_WARPS * 32, KS_LARGE_WARPS * KS_LARGE_BUF * sizeof(double), s>>>(
             n0, n1, h, p_out, w, NCB_KS_KIND_LARGE);
     int tblocks = (int)((nprob + KS_SMALL_THREADS - 1) / KS_SMALL_THREADS);

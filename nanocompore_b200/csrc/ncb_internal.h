@@ -59,11 +59,12 @@ struct NcbWorklists {
 #define NCB_KS_BUCKETS 64      /* cost buckets per kind (2 per octave of cost)           */
 enum { NCB_KS_KIND_SMALL = 0,  /* unequal sizes, DP window <= NCB_KS_SMALL_WINDOW: thread per problem */
        NCB_KS_KIND_EQUAL = 1,  /* equal sizes: Horner product, thread per problem        */
-       NCB_KS_KIND_LARGE = 2,  /* unequal sizes, min(n0,n1) < 1024: warp wavefront       */
-       NCB_KS_KIND_HUGE = 3,   /* unequal sizes, min(n0,n1) >= 1024: warp wavefront, big buffer */
+       NCB_KS_KIND_LARGE = 2,  /* unequal sizes, band span <= 1024 columns: warp wavefront, 8 KB ring */
+       NCB_KS_KIND_HUGE = 3,   /* unequal sizes, wider band: warp wavefront, full row (41 KB) per warp */
        NCB_KS_KINDS = 4 };
 #define NCB_KS_SMALL_WINDOW 64
-#define NCB_KS_LARGE_MAXN 1023
+#define NCB_KS_RING_SMALL 1024   /* doubles in the ring of the LARGE kind */
+#define NCB_KS_RING_FULL (NCB_MAX_READS / 2 + 1)   /* the HUGE kind holds the whole row: no wrap */
 #define NCB_KS_NBINS (NCB_KS_KINDS * NCB_KS_BUCKETS)
 
 struct NcbKsWork {
