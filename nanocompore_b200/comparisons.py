@@ -118,14 +118,46 @@ class TranscriptComparator:
                 f"data has {data.shape[2]} variables, motor_dwell_offset = {self._motor_dwell_offset}")
 
         engine = self._engine(device)
-        pos_host = positions.cpu() if isinstance(positions, torch.Tensor) else torch.as_tensor(positions)
-        results = pd.DataFrame({'transcript_id': transcript.id, 'pos': pos_host})
-
         self._worker.log("trace", "Start comparison kernels")
         dev_data = torch.as_tensor(data).to(device=engine.device, dtype=torch.float32).contiguous()
         labels = torch.from_numpy(make_labels(_to_numpy(samples), _to_numpy(conditions))).to(engine.device)
         res = engine.compare_dense(dev_data, labels).numpy()
-        status, pv, st, counts = res['status'], res['pvalues'], res['stats'], res['counts']
+        return transcript, self._assemble(transcript, positions, res['status'], res['pvalues'],
+                                          res['stats'], res['counts'], with_motor)
+
+    def compare_transcripts(self, items, device):
+        """
+        Batch form of ``compare_transcript`` (an extension; the reference has no batch call):
+        ``items`` is a list of ``(transcript, data, samples, conditions, positions)`` as
+        ``compare_transcript`` takes them.  All transcripts are packed into ONE ragged batch by
+        libncb's host packer and go through ONE ``ncb_compare`` call; the result is the list of
+        ``(transcript, DataFrame | None)`` the per-transcript calls would give.
+        """
+        from nanocompore_b200.engine import pack_csr
+        with_motor = self._motor_dwell_offset > 0
+        live = [(i, it) for i, it in enumerate(items) if len(it[4]) > 0]
+        out = [(it[0], None) for it in items]
+        if not live:
+            return out
+        if with_motor:          # the packer writes 2 variables: 3-variable batches go one by one
+            for i, (tr, data, samples, conditions, positions) in live:
+                out[i] = self.compare_transcript(tr, data, samples, conditions, positions, device)
+            return out
+        engine = self._engine(device)
+        batch, ptx, _ = pack_csr([(_to_numpy(d).astype(np.float32, copy=False), _to_numpy(s), _to_numpy(c))
+                                  for _, (_, d, s, c, _) in live], pin=True)
+        res = engine.compare_csr(batch).numpy()
+        for k, (i, (tr, data, samples, conditions, positions)) in enumerate(live):
+            sel = ptx == k
+            out[i] = (tr, self._assemble(tr, positions, res['status'][sel], res['pvalues'][:, sel],
+                                         res['stats'][:, sel], res['counts'][:, :, sel], with_motor))
+        return out
+
+    def _assemble(self, transcript, positions, status, pv, st, counts, with_motor):
+        """Result frame of one transcript from its slice of the result columns
+        (comparisons.py:83-84, 108-148, 204-215)."""
+        pos_host = positions.cpu() if isinstance(positions, torch.Tensor) else torch.as_tensor(positions)
+        results = pd.DataFrame({'transcript_id': transcript.id, 'pos': pos_host})
         if (status & L.NCB_POS_TOO_MANY_READS).any():
             raise NanocomporeError(
                 f"A position of transcript {transcript.name} has more than {L.NCB_MAX_READS} reads; "
@@ -162,7 +194,7 @@ class TranscriptComparator:
             for test in tests:
                 results[f"{test}_context_{context}"] = self._combine_context_pvalues(results, test)
 
-        return transcript, results
+        return results
 
     def _get_test_masks(self, auto_test_mask, n_positions):
         # comparisons.py:150-162; iteration order is the config order (the reference iterates

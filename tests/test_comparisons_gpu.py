@@ -176,3 +176,30 @@ def test_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
         compare(config(comparison_methods=['GOF']), np.zeros((2, 8, 2), np.float32), np.zeros(8), np.zeros(8),
                 np.arange(2, dtype=np.int16))
+
+
+def test_batch_call_equals_per_transcript_calls():
+    """compare_transcripts: one packed batch, one libncb call, same frames (fixture config 1 + synthetic)."""
+    z = load('fixture_cfg1.npz')
+    items = []
+    for ti in range(int(z['n_transcripts'])):
+        data, samples, conditions, positions = oprep.prepare_data(
+            z[f'tx{ti}/raw'], z[f'tx{ti}/sample_ids'], z[f'tx{ti}/condition_ids'])
+        data, positions = oprep.filter_low_cov_positions(data, positions, conditions, 1)
+        items.append((Transcript(ti, f'tx{ti}'), torch.from_numpy(data), torch.as_tensor(samples),
+                      torch.as_tensor(conditions), torch.as_tensor(positions)))
+    s = load('synthetic_ref.npz')
+    items.append((Transcript(7, 'syn'), torch.from_numpy(s['case1/prepared']), torch.as_tensor(s['case1/samples']),
+                  torch.as_tensor(s['case1/conditions']), torch.as_tensor(s['case1/prepared_positions'])))
+    items.append((Transcript(8, 'empty'), torch.zeros((0, 4, 2)), torch.zeros(4), torch.zeros(4),
+                  torch.zeros(0, dtype=torch.int16)))
+    cmp_ = TranscriptComparator(config(), Worker())
+    batch = cmp_.compare_transcripts(items, 'cuda:0')
+    assert batch[-1][1] is None and len(batch) == len(items)
+    rows = 0
+    for (tr, df), item in zip(batch[:-1], items[:-1]):
+        one = cmp_.compare_transcript(*item, 'cuda:0')[1]
+        assert tr is item[0] and list(df.columns) == list(one.columns)
+        pd.testing.assert_frame_equal(df.reset_index(drop=True), one.reset_index(drop=True))
+        rows += len(df)
+    assert rows == 3519 + len(s['case1/result/pos'])
