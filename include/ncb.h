@@ -233,6 +233,57 @@ int ncb_pack_fill(const float *data, const uint8_t *label, int64_t n_positions, 
                   int32_t n_vars, const int64_t *pos_offsets, float *signal_out, uint8_t *label_out,
                   int threads);
 
+/* --- transcript readers (host code) ---------------------------------------
+ * Planar rows: one read = intensity[n_positions] + dwell[n_positions] float32, NaN where the
+ * read does not cover the position.  This is what the reference's SQLite store keeps per read
+ * (signal_data blobs, database.py:69-76, decoded at run.py:795-801) and what
+ * ncb_bam_read_uncalled4 decodes from Uncalled4 BAM tags; ncb_pack_rows_* turn the rows of all
+ * samples of a transcript into the CSR arrays of ncb_compare without building the dense
+ * (positions, reads, vars) tensor of GenericWorker._read_data / Uncalled4.get_data
+ * (run.py:833-838, uncalled4.py:80-115).
+ *
+ * ncb_pack_rows_count / ncb_pack_rows_fill: rows are passed as arrays of row pointers (so SQLite
+ * blobs are used in place, and ordering / filtering reads is a permutation of pointers), in the
+ * read order the fit must see (run.py:698-700, 820-826).  motor_offset > 0 adds the third
+ * variable of Worker._prepare_data (run.py:575-584) -- the raw dwell of the same read
+ * motor_offset positions downstream -- and the output has 3 floats per entry.  A read is kept at
+ * a position when any of its variables is a number.  Two passes like ncb_pack_count/_fill. */
+int ncb_pack_rows_count(const float *const *intensity, const float *const *dwell, int64_t n_rows,
+                        int64_t n_positions, int32_t motor_offset, int64_t *counts, int threads);
+int ncb_pack_rows_fill(const float *const *intensity, const float *const *dwell,
+                       const uint8_t *row_label, int64_t n_rows, int64_t n_positions,
+                       int32_t motor_offset, const int64_t *pos_offsets, float *signal_out,
+                       uint8_t *label_out, int threads);
+/* common.get_reads_invalid_ratio (common.py:298-329): per row, the share of positions between
+ * its first and last valid intensity that are NaN; NaN for a row without any valid position. */
+int ncb_rows_invalid_ratio(const float *const *intensity, int64_t n_rows, int64_t n_positions,
+                           double *ratios, int threads);
+
+/* BGZF/BAM reader with the Uncalled4 tag decoder: replaces pysam.AlignmentFile.fetch/count and
+ * Uncalled4.get_data/_copy_signal_to_tensor/_resolve_skips (uncalled4.py:57-201) for one
+ * reference (transcript).  ncb_bam_open indexes the file in one pass (`threads` inflate BGZF
+ * blocks in parallel); no .bai is needed.  On failure ncb_bam_open may still return a handle so
+ * that ncb_bam_last_error can be read; close it. */
+typedef struct ncb_bam ncb_bam;
+int ncb_bam_open(ncb_bam **out, const char *path, int threads);
+void ncb_bam_close(ncb_bam *b);
+const char *ncb_bam_last_error(const ncb_bam *b);
+int32_t ncb_bam_n_references(const ncb_bam *b);
+const char *ncb_bam_reference_name(const ncb_bam *b, int32_t i);
+int64_t ncb_bam_reference_length(const ncb_bam *b, int32_t i);
+/* every record placed on the reference, secondary and supplementary included
+ * (pysam's count(reference=...), uncalled4.py:76-77): the capacity to allocate */
+int64_t ncb_bam_reference_records(const ncb_bam *b, int32_t i);
+int32_t ncb_bam_reference_index(const ncb_bam *b, const char *name);   /* -1: not in the header */
+/* Decodes the primary reads of reference `ref`: read k fills intensity[k*ref_len ..] and
+ * dwell[k*ref_len ..] (NaN elsewhere; the int16 value -32768 is Uncalled4's NaN) and
+ * names[k*name_stride ..] (NUL-terminated query name).  kit_len / kit_center: the pore model
+ * (common.py:29-32: RNA002 5/4, RNA004 9/5).  Returns the number of reads decoded (file order),
+ * or a negative ncb_status (message in ncb_bam_last_error). */
+int64_t ncb_bam_read_uncalled4(ncb_bam *b, int32_t ref, int64_t ref_len, int32_t kit_len,
+                               int32_t kit_center, float *intensity, float *dwell, char *names,
+                               int32_t name_stride, int64_t max_reads);
+
 /* --- introspection ---------------------------------------------------------------- */
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */

@@ -47,7 +47,10 @@ NCB_DF_ROWS = 17
 EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
            'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals',
-           'ncb_pack_count', 'ncb_pack_fill']
+           'ncb_pack_count', 'ncb_pack_fill', 'ncb_pack_rows_count', 'ncb_pack_rows_fill',
+           'ncb_rows_invalid_ratio', 'ncb_bam_open', 'ncb_bam_close', 'ncb_bam_last_error',
+           'ncb_bam_n_references', 'ncb_bam_reference_name', 'ncb_bam_reference_length',
+           'ncb_bam_reference_records', 'ncb_bam_reference_index', 'ncb_bam_read_uncalled4']
 
 
 class NcbOpts(C.Structure):
@@ -122,6 +125,30 @@ def load(path=None):
     lib.ncb_pack_count.restype = C.c_int
     lib.ncb_pack_fill.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, C.c_int]
     lib.ncb_pack_fill.restype = C.c_int
+    lib.ncb_pack_rows_count.argtypes = [vp, vp, i64, i64, i32, vp, C.c_int]
+    lib.ncb_pack_rows_count.restype = C.c_int
+    lib.ncb_pack_rows_fill.argtypes = [vp, vp, vp, i64, i64, i32, vp, vp, vp, C.c_int]
+    lib.ncb_pack_rows_fill.restype = C.c_int
+    lib.ncb_rows_invalid_ratio.argtypes = [vp, i64, i64, vp, C.c_int]
+    lib.ncb_rows_invalid_ratio.restype = C.c_int
+    lib.ncb_bam_open.argtypes = [C.POINTER(vp), C.c_char_p, C.c_int]
+    lib.ncb_bam_open.restype = C.c_int
+    lib.ncb_bam_close.argtypes = [vp]
+    lib.ncb_bam_close.restype = None
+    lib.ncb_bam_last_error.argtypes = [vp]
+    lib.ncb_bam_last_error.restype = C.c_char_p
+    lib.ncb_bam_n_references.argtypes = [vp]
+    lib.ncb_bam_n_references.restype = i32
+    lib.ncb_bam_reference_name.argtypes = [vp, i32]
+    lib.ncb_bam_reference_name.restype = C.c_char_p
+    lib.ncb_bam_reference_length.argtypes = [vp, i32]
+    lib.ncb_bam_reference_length.restype = i64
+    lib.ncb_bam_reference_records.argtypes = [vp, i32]
+    lib.ncb_bam_reference_records.restype = i64
+    lib.ncb_bam_reference_index.argtypes = [vp, C.c_char_p]
+    lib.ncb_bam_reference_index.restype = i32
+    lib.ncb_bam_read_uncalled4.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, i32, i64]
+    lib.ncb_bam_read_uncalled4.restype = i64
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
     _libs[path] = lib

@@ -153,6 +153,31 @@ class TranscriptComparator:
                                          res['stats'][:, sel], res['counts'][:, :, sel], with_motor))
         return out
 
+    def compare_packed(self, batch, device, min_coverage=0, dwell_is_raw=True):
+        """
+        Entry of the reader pipeline (``readers.TranscriptPipeline``): one ragged CSR batch as
+        ``readers.pack_rows`` builds it -- RAW dwell times, every position of every transcript --
+        through one ``ncb_compare`` call.  The log10 of run.py:573 and the coverage filter of
+        run.py:511-515 run inside the statistics kernel.  Returns the result columns as numpy
+        arrays, one slot per position of the batch (``status`` carries the filter's verdict).
+        """
+        with_motor = self._motor_dwell_offset > 0
+        if batch.signal.shape[1] != (3 if with_motor else 2):
+            raise NanocomporeError(
+                f"batch has {batch.signal.shape[1]} variables, motor_dwell_offset = {self._motor_dwell_offset}")
+        engine = self._engine(device)
+        engine.configure(min_coverage=min_coverage, dwell_is_raw=dwell_is_raw)
+        try:
+            return engine.compare_csr(batch).numpy()
+        finally:
+            engine.configure(min_coverage=0, dwell_is_raw=False)
+
+    def assemble(self, transcript, positions, status, pv, st, counts):
+        """Result frame of one transcript from its slice of the result columns of a batch."""
+        if len(positions) == 0:
+            return None
+        return self._assemble(transcript, positions, status, pv, st, counts, self._motor_dwell_offset > 0)
+
     def _assemble(self, transcript, positions, status, pv, st, counts, with_motor):
         """Result frame of one transcript from its slice of the result columns
         (comparisons.py:83-84, 108-148, 204-215)."""

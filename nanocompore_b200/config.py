@@ -9,6 +9,8 @@ without the reference installed (its ``Config`` needs the ``schema`` package).
 DEFAULT_MIN_COVERAGE = 30
 DEFAULT_DOWNSAMPLE_HIGH_COVERAGE = 5000
 DEFAULT_COMPARISON_METHODS = ['GMM', 'KS']
+DEFAULT_KIT = 'RNA002'
+DEFAULT_MAX_INVALID_KMERS_FREQ = 0.1
 HARD_ASSIGNMENT = 'hard'
 SOFT_ASSIGNMENT = 'soft'
 
@@ -77,6 +79,25 @@ class PathConfig:
 
     def sample_to_condition(self):
         return {sample: cond for cond, samples in self.get_data().items() for sample in samples}
+
+    # ---- keys read by the transcript readers (run.py:657-855) --------------------------------
+    def get_kit(self):
+        """config.py:244-250; returns the kit NAME ('RNA002' / 'RNA004'), which is also what
+        ``readers.kit_geometry`` accepts from the reference's ``Kit`` enum (``kit.name``)."""
+        return self._config.get('kit', DEFAULT_KIT)
+
+    def get_max_invalid_kmers_freq(self):
+        return self._config.get('max_invalid_kmers_freq', DEFAULT_MAX_INVALID_KMERS_FREQ)
+
+    def get_sample_condition_bam_data(self):
+        return [(sample, condition, samp_def['bam'])
+                for condition, samples in self.get_data().items()
+                for sample, samp_def in samples.items()]
+
+    def get_sample_condition_db_data(self):
+        return [(sample, condition, samp_def['db'])
+                for condition, samples in self.get_data().items()
+                for sample, samp_def in samples.items()]
 
     def is_multi_replicate(self):
         return all(len(reps) > 1 for reps in self.get_data().values())

@@ -76,4 +76,81 @@ int ncb_pack_fill(const float *data, const uint8_t *label, int64_t n_positions, 
     return NCB_OK;
 }
 
+// ---- planar read-major rows -> CSR ---------------------------------------------------------
+// Rows are what the readers produce per read: intensity[n_positions], dwell[n_positions] with NaN
+// where the read does not cover the position (SQLite signal_data blobs, run.py:795-801, used in
+// place; rows decoded from Uncalled4 BAM tags by ncb_bam_read_uncalled4).  The dense
+// (positions, reads, vars) tensor of the reference (run.py:833-838: concatenate, transpose,
+// stack) is never built.  Threads own tiles of positions; inside a tile the rows are walked in
+// row order, so the reads of a position keep the row order (the order the mixture fit sees).
+// motor_offset > 0 adds the third variable of Worker._prepare_data (run.py:575-584): the dwell of
+// the same read `motor_offset` positions downstream.
+
+namespace {
+const int64_t ROW_TILE = 512;   // positions per tile: 2 KB of every row, cursors stay in L1
+
+inline bool is_num(float x) { return x == x; }
+}  // namespace
+
+int ncb_pack_rows_count(const float *const *intensity, const float *const *dwell, int64_t n_rows,
+                        int64_t n_positions, int32_t motor_offset, int64_t *counts, int threads) {
+    if (n_rows < 0 || n_positions < 0 || motor_offset < 0 || (n_positions > 0 && !counts) ||
+        (n_rows > 0 && (!intensity || !dwell)))
+        return NCB_ERR_INVALID;
+    const int64_t tiles = (n_positions + ROW_TILE - 1) / ROW_TILE;
+    parallel_for(tiles, threads, [=](int64_t t_lo, int64_t t_hi) {
+        for (int64_t t = t_lo; t < t_hi; ++t) {
+            const int64_t p0 = t * ROW_TILE, p1 = p0 + ROW_TILE < n_positions ? p0 + ROW_TILE : n_positions;
+            int64_t c[ROW_TILE];
+            for (int64_t i = 0; i < p1 - p0; ++i) c[i] = 0;
+            for (int64_t r = 0; r < n_rows; ++r) {
+                const float *x = intensity[r], *y = dwell[r];
+                for (int64_t p = p0; p < p1; ++p) {
+                    bool keep = is_num(x[p]) || is_num(y[p]);
+                    if (motor_offset > 0 && p + motor_offset < n_positions) keep |= is_num(y[p + motor_offset]);
+                    c[p - p0] += keep ? 1 : 0;
+                }
+            }
+            for (int64_t i = 0; i < p1 - p0; ++i) counts[p0 + i] = c[i];
+        }
+    });
+    return NCB_OK;
+}
+
+int ncb_pack_rows_fill(const float *const *intensity, const float *const *dwell, const uint8_t *row_label,
+                       int64_t n_rows, int64_t n_positions, int32_t motor_offset,
+                       const int64_t *pos_offsets, float *signal_out, uint8_t *label_out, int threads) {
+    if (n_rows < 0 || n_positions < 0 || motor_offset < 0 ||
+        (n_positions > 0 && (!pos_offsets || !signal_out || !label_out)) ||
+        (n_rows > 0 && (!intensity || !dwell || !row_label)))
+        return NCB_ERR_INVALID;
+    const int V = motor_offset > 0 ? 3 : 2;
+    const float NaN = nanf("");
+    const int64_t tiles = (n_positions + ROW_TILE - 1) / ROW_TILE;
+    parallel_for(tiles, threads, [=](int64_t t_lo, int64_t t_hi) {
+        for (int64_t t = t_lo; t < t_hi; ++t) {
+            const int64_t p0 = t * ROW_TILE, p1 = p0 + ROW_TILE < n_positions ? p0 + ROW_TILE : n_positions;
+            int64_t cur[ROW_TILE];
+            for (int64_t i = 0; i < p1 - p0; ++i) cur[i] = pos_offsets[p0 + i];
+            for (int64_t r = 0; r < n_rows; ++r) {
+                const float *x = intensity[r], *y = dwell[r];
+                const uint8_t lab = row_label[r];
+                for (int64_t p = p0; p < p1; ++p) {
+                    const float xv = x[p], yv = y[p];
+                    float mv = NaN;
+                    if (motor_offset > 0 && p + motor_offset < n_positions) mv = y[p + motor_offset];
+                    if (is_num(xv) || is_num(yv) || is_num(mv)) {
+                        const int64_t o = cur[p - p0]++;
+                        signal_out[V * o] = xv;
+                        signal_out[V * o + 1] = yv;
+                        if (V == 3) signal_out[V * o + 2] = mv;
+                        label_out[o] = lab;
+                    }
+                }
+            }
+        }
+    });
+    return NCB_OK;
+}
+
 }  // extern "C"

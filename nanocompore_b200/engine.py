@@ -47,7 +47,8 @@ def make_labels(samples, conditions):
 class CsrBatch:
     """Ragged batch: the valid reads of each position, position after position.
 
-    pos_offsets int64 [P+1]; signal float32 [E, 2] {intensity, dwell}; label uint8 [E].
+    pos_offsets int64 [P+1]; signal float32 [E, V] {intensity, dwell[, motor dwell]}, V = 2 or 3;
+    label uint8 [E].
     Tensors are either all pinned-host or all on the device."""
     pos_offsets: torch.Tensor
     signal: torch.Tensor
@@ -285,6 +286,7 @@ class Engine:
         b.pos_offsets = batch.pos_offsets.data_ptr()
         b.signal = batch.signal.data_ptr()
         b.label = batch.label.data_ptr()
+        b.n_vars = batch.signal.shape[1]     # 2, or 3 with the motor-dwell column
         r = results.struct()
         s = self._stream(stream)
         self._check(self.lib.ncb_compare(self._handle, C.byref(b), C.byref(r), s))

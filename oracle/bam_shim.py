@@ -3,7 +3,7 @@ Minimal stdlib BAM reader with the slice of the pysam API the reference's Uncall
 uses (``AlignmentFile.fetch / count``, ``read.get_tag / query_name / is_secondary /
 is_supplementary``).  pysam is not installed in the build container; this shim lets
 /root/reference/nanocompore/uncalled4.py run UNMODIFIED over the reference's fixture BAMs
-when the golden vectors are generated (tests/golden/make_golden.py).  Test infrastructure.
+when the golden vectors are generated (tests/golden/make_golden.py), and oracle/readers.py.  Test infrastructure.
 """
 import gzip
 import struct

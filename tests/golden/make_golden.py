@@ -6,7 +6,7 @@ Generates the golden fixtures under tests/golden/ by running the UNMODIFIED refe
 
 Outputs (committed; /root/reference does not exist on the GPU box):
   fixture_cfg1.npz      BASELINE config 1: the reference's bundled fixture BAMs read by the
-                        reference's own Uncalled4 parser (through tests/golden/bam_shim.py),
+                        reference's own Uncalled4 parser (through oracle/bam_shim.py),
                         the raw per-transcript tensors, and the result columns of the
                         reference's compare_transcript with the default methods [GMM, KS]
   synthetic_ref.npz     seeded synthetic transcripts and the reference's result columns for
@@ -61,7 +61,7 @@ def read_fasta(path):
 
 def fixture_config1(ref):
     import torch
-    import bam_shim
+    from oracle import bam_shim
     from nanocompore.uncalled4 import Uncalled4
     from nanocompore.common import get_reads_invalid_ratio, INTENSITY_POS
     from nanocompore.run import Worker
