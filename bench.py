@@ -299,6 +299,7 @@ def run_gpu_arm(args):
         eng.compare_csr(dev_batches[b], res_dev[0], wait=False)
     totals = eng.timing_totals()
     eng.set_timing(False)
+    fp64_peak = eng.probe_fp64_peak()   # DFMA microbenchmark on this device, TFLOP/s
 
     # ---- e2e: pinned host batches through the public API, copies inside the timed region ---
     res_host = [Results(P, 4, None) for _ in range(NSLOT)]
@@ -369,7 +370,30 @@ def run_gpu_arm(args):
                 "ms_ks_pvalue_kernels": totals['ms_ks'] / nb,
                 "ms_classify": totals['ms_classify'] / nb,
                 "note": "both kernels are issue / fp64-pipe bound (fp64 EM, sort), not HBM bound: "
-                        "DRAM traffic equals the algorithmic bytes and is ~1 % of peak; see DESIGN.md"}
+                        "DRAM traffic equals the algorithmic bytes and is ~1 % of peak; the fp64 entry "
+                        "is the compute roofline of the mixture kernel; see DESIGN.md"}
+    # compute roofline of the same kernel: fp64 operations per position counted by ncu
+    # (profiles/fp64_ops.json, thread-level DFMA/DADD/DMUL of the --set full capture) x the
+    # positions of a launch / the live launch time, against the fp64 rate measured by
+    # ncb_probe_fp64_peak in this run
+    ops_path = os.path.join(ROOT, 'profiles', 'fp64_ops.json')
+    fp64 = {"peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured (DFMA microbenchmark, this run)",
+            "achieved": None, "frac": None}
+    if os.path.exists(ops_path):
+        try:
+            with open(ops_path) as f:
+                ops = json.load(f)
+            flop = (2.0 * ops["dfma_per_position"] + ops["dadd_per_position"] + ops["dmul_per_position"]) * P
+            slots = (ops["dfma_per_position"] + ops["dadd_per_position"] + ops["dmul_per_position"]) * P
+            fp64["achieved"] = flop / (ms_gmm / 1000.0) / 1e12
+            fp64["frac"] = fp64["achieved"] / fp64_peak
+            # share of the fp64 pipe's issue slots (an add or a multiply takes the slot of an FMA)
+            fp64["pipe_frac"] = 2.0 * slots / (ms_gmm / 1000.0) / 1e12 / fp64_peak
+            fp64["flop_per_position"] = flop / P
+            fp64["ops_source"] = ops.get("source")
+        except Exception:
+            pass
+    roofline["fp64"] = fp64
     ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(ncu_traffic):
         try:

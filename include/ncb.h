@@ -299,6 +299,11 @@ int ncb_last_timing(ncb_handle *h, float *ms_position_kernels, float *ms_ks_kern
 int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_stats,
                       double *ms_gmm, double *ms_ks);
 
+/* Non-tensor fp64 rate of the device in TFLOP/s, measured with a register-resident DFMA
+ * microbenchmark (best of 3 after a warm-up): the compute roofline the fp64 mixture kernel is
+ * reported against in bench.py. */
+int ncb_probe_fp64_peak(ncb_handle *h, double *tflops, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,7 +50,8 @@ EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 
            'ncb_pack_count', 'ncb_pack_fill', 'ncb_pack_rows_count', 'ncb_pack_rows_fill',
            'ncb_rows_invalid_ratio', 'ncb_bam_open', 'ncb_bam_close', 'ncb_bam_last_error',
            'ncb_bam_n_references', 'ncb_bam_reference_name', 'ncb_bam_reference_length',
-           'ncb_bam_reference_records', 'ncb_bam_reference_index', 'ncb_bam_read_uncalled4']
+           'ncb_bam_reference_records', 'ncb_bam_reference_index', 'ncb_bam_read_uncalled4',
+           'ncb_probe_fp64_peak']
 
 
 class NcbOpts(C.Structure):
@@ -149,6 +150,8 @@ def load(path=None):
     lib.ncb_bam_reference_index.restype = i32
     lib.ncb_bam_read_uncalled4.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, i32, i64]
     lib.ncb_bam_read_uncalled4.restype = i64
+    lib.ncb_probe_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
+    lib.ncb_probe_fp64_peak.restype = C.c_int
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
     _libs[path] = lib

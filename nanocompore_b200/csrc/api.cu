@@ -492,4 +492,47 @@ int ncb_last_timing(ncb_handle *h, float *ms_position, float *ms_ks, float *ms_t
     return NCB_OK;
 }
 
+// Measures the non-tensor fp64 rate of the device: every thread runs 8 independent chains of
+// dependent DFMAs held in registers (no memory traffic), 8 CTAs of 256 threads per SM.  This is
+// the compute roofline of the mixture kernel (fp64 EM), reported next to the HBM one.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, double a, double b, int iters) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3,
+           x4 = x0 + 4e-3, x5 = x0 + 5e-3, x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;   // keeps the chains alive
+}
+
+int ncb_probe_fp64_peak(ncb_handle *h, double *tflops, void *stream) {
+    if (!h || !tflops) return NCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ENSURE(h->unit_a, 256);
+    const int iters = 1 << 16, blocks = h->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {   // the first repetition warms the clocks up
+        CK(cudaEventRecord(e0, s));
+        fp64_probe_kernel<<<blocks, threads, 0, s>>>((double *)h->unit_a.ptr, 0.999999, 1e-7, iters);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double t = 2.0 * 8.0 * (double)iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t > best) best = t;
+        ++h->launches;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return NCB_OK;
+}
+
 }  // extern "C"

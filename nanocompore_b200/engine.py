@@ -364,6 +364,12 @@ class Engine:
         self._check(self.lib.ncb_last_timing(self._handle, C.byref(a), C.byref(b), C.byref(c)))
         return dict(ms_position=a.value, ms_ks=b.value, ms_total=c.value)
 
+    def probe_fp64_peak(self):
+        """Measured non-tensor fp64 rate of the device in TFLOP/s (DFMA microbenchmark)."""
+        t = C.c_double()
+        self._check(self.lib.ncb_probe_fp64_peak(self._handle, C.byref(t), self._stream()))
+        return t.value
+
     def timing_totals(self):
         """Sums of the CUDA-event timings of every batch since ``set_timing(True)``."""
         n, a, b, c, d = C.c_int64(), C.c_double(), C.c_double(), C.c_double(), C.c_double()

@@ -58,8 +58,9 @@ UNITS = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
 
 
 def short_name(name):
+    name = name.replace('(int)', '').replace('(bool)', '')
     base = name.split('(')[0].replace('void ', '').split('::')[-1]
-    return base.replace('<', '_').replace('>', '').replace(', ', '_').replace(' ', '').replace('(int)', '').replace('(bool)', '')
+    return base.replace('<', '_').replace('>', '').replace(', ', '_').replace(' ', '')
 
 
 def full(tag, rep):

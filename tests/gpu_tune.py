@@ -1,4 +1,4 @@
-"""Times builds of libncb (build/variants/*.so) on the config-3 batch shape; tuning helper.
+"""Times builds of libncb (build/tune/*.so) on the config-3 batch shape; tuning helper.
 
     python tests/gpu_tune.py [n_transcripts] [lib ...]
 """
@@ -15,7 +15,7 @@ from bench import make_batch_transcripts  # noqa: E402
 from nanocompore_b200.engine import Engine, Results, pack_csr  # noqa: E402
 
 n_tx = int(sys.argv[1]) if len(sys.argv) > 1 else 25
-libs = sys.argv[2:] or sorted(glob.glob(os.path.join(ROOT, 'build', 'variants', '*.so')))
+libs = sys.argv[2:] or sorted(glob.glob(os.path.join(ROOT, 'build', 'tune', '*.so')))
 batches = []
 for b in range(3):
     txs = make_batch_transcripts(555 + b, n_tx)
