@@ -15,6 +15,19 @@ namespace ncb {
 
 NCB_HD inline double ncb_nan() { return nan(""); }
 
+// a / b from rb = RN(1 / b): q = RN(a rb), r = a - b q (exact in an fma), RN(q + r rb).  With a
+// correctly rounded reciprocal this is the correctly rounded quotient (Markstein), i.e. the bits
+// of the division, for 3 operations; several quotients by one divisor share the reciprocal.
+// Operands must be normal numbers whose quotient is normal (no range handling).
+NCB_HD inline double quot_rn(double a, double b, double rb) {
+#if defined(__CUDA_ARCH__)
+    const double q = __dmul_rn(a, rb);
+#else
+    const double q = a * rb;
+#endif
+    return fma(fma(-b, q, a), rb, q);
+}
+
 NCB_HD inline double clip01(double p) {
     // np.clip keeps NaN
     if (p != p) return p;

@@ -15,5 +15,8 @@ double hc_chi2_2x2_p(double a, double b, double c, double d) { return ncb::chi2_
 void hc_logit_wald(double a, double b, double c, double d, double *coef, double *p) { ncb::logit_wald(a, b, c, d, coef, p); }
 double hc_ks_prob_outside_square(long long n, long long h) { return ncb::ks_prob_outside_square(n, h); }
 double hc_ks_equal_p(long long n, long long h) { return ncb::ks_equal_p(n, h); }
+void hc_quot_rn(const double *a, const double *b, double *q, long long n) {
+    for (long long i = 0; i < n; ++i) q[i] = ncb::quot_rn(a[i], b[i], 1.0 / b[i]);
+}
 double hc_normal_two_sided(double z) { return ncb::normal_two_sided(z); }
 }

@@ -34,6 +34,7 @@ def hc():
     lib.hc_ks_prob_outside_square.restype = d; lib.hc_ks_prob_outside_square.argtypes = [ll, ll]
     lib.hc_ks_equal_p.restype = d; lib.hc_ks_equal_p.argtypes = [ll, ll]
     lib.hc_normal_two_sided.restype = d; lib.hc_normal_two_sided.argtypes = [d]
+    lib.hc_quot_rn.restype = None; lib.hc_quot_rn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, ll]
     return lib
 
 
@@ -148,3 +149,21 @@ def test_ks_equal_sizes_with_scipy_fallback(hc):
     a = np.arange(7.0)
     b = np.arange(7.0) + 0.5
     assert abs(hc.hc_ks_equal_p(7, 1) - stats.ks_2samp(a, b).pvalue) < 1e-15
+
+
+def test_quotient_from_reciprocal_is_the_division(hc):
+    """quot_rn(a, b, RN(1/b)) -- the 3-operation quotient the M-step and the exact-KS recurrence
+    use -- has the bits of a / b (Markstein), including divisors with an all-ones mantissa."""
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 8, n)
+    b = rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 8, n)
+    b[b == 0] = 1.0
+    # adversarial divisors: mantissa all ones / nearly so, and small integers
+    k = n // 10
+    b[:k] = np.ldexp(2.0 - np.ldexp(rng.integers(1, 64, k).astype(np.float64), -52), rng.integers(-20, 20, k))
+    b[k:2 * k] = rng.integers(1, 400, k).astype(np.float64)
+    a[k:2 * k] = rng.integers(1, 10 ** 6, k).astype(np.float64) * 0.1
+    q = np.empty(n)
+    hc.hc_quot_rn(a.ctypes.data, b.ctypes.data, q.ctypes.data, n)
+    assert np.array_equal(q, a / b)
