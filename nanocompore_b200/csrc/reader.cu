@@ -19,6 +19,10 @@
 // A coordinate-sorted BAM has one run per reference, so reading a transcript inflates only the
 // blocks that hold its records; no .bai is needed and unsorted files work too.
 #include <errno.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -56,7 +60,7 @@ inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
 
 struct ncb_bam {
     std::string path;
-    FILE *f = nullptr;
+    const uint8_t *map = nullptr;   // the whole file, read-only mapping
     int64_t file_size = 0;
     int threads = 1;
     std::string error;
@@ -70,27 +74,27 @@ struct ncb_bam {
     // ---- block access ---------------------------------------------------------------------
     // Reads the header of the BGZF member at `off`; false at a clean end of file.
     bool block_at(int64_t off, Block &b) {
-        uint8_t h[18];
         if (off >= file_size) return false;
-        if (fseeko(f, off, SEEK_SET) != 0 || fread(h, 1, 18, f) != 18) {
+        if (off + 18 > file_size) {
             error = "truncated BGZF block header";
             return false;
         }
+        const uint8_t *h = map + off;
         if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) {
             error = "not a BGZF block (gzip member without the BC extra field)";
             return false;
         }
         const int xlen = rd16(h + 10);
-        // the BC subfield is normally first; walk the extra field to be safe
-        std::vector<uint8_t> extra(xlen);
-        if (fseeko(f, off + 12, SEEK_SET) != 0 || fread(extra.data(), 1, xlen, f) != (size_t)xlen) {
+        if (off + 12 + xlen > file_size) {
             error = "truncated BGZF extra field";
             return false;
         }
+        // the BC subfield is normally first; walk the extra field to be safe
+        const uint8_t *extra = h + 12;
         int bsize = -1;
         for (int i = 0; i + 4 <= xlen;) {
             const int slen = rd16(&extra[i + 2]);
-            if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2) bsize = rd16(&extra[i + 4]);
+            if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = rd16(&extra[i + 4]);
             i += 4 + slen;
         }
         if (bsize < 0) {
@@ -99,32 +103,23 @@ struct ncb_bam {
         }
         b.file_off = off;
         b.csize = bsize + 1;
-        uint8_t tail[4];
-        if (fseeko(f, off + b.csize - 4, SEEK_SET) != 0 || fread(tail, 1, 4, f) != 4) {
+        if (off + b.csize > file_size || b.csize < 12 + xlen + 8) {
             error = "truncated BGZF block";
             return false;
         }
-        b.usize = (int32_t)rd32(tail);
+        b.usize = (int32_t)rd32(h + b.csize - 4);
         return true;
     }
 
-    // Inflates the members described by `blocks` (their compressed bytes are contiguous in the
-    // file) into out[i]; `threads` inflate in parallel.
+    // Inflates the members described by `blocks` into out[i]; `threads` inflate in parallel.
     bool inflate_blocks(const std::vector<Block> &blocks, std::vector<std::vector<uint8_t>> &out) {
         if (blocks.empty()) return true;
-        const int64_t lo = blocks.front().file_off;
-        const int64_t hi = blocks.back().file_off + blocks.back().csize;
-        std::vector<uint8_t> comp((size_t)(hi - lo));
-        if (fseeko(f, lo, SEEK_SET) != 0 || fread(comp.data(), 1, comp.size(), f) != comp.size()) {
-            error = "short read of BGZF blocks";
-            return false;
-        }
         out.assign(blocks.size(), {});
         std::vector<int> ok(blocks.size(), 1);
         auto work = [&](size_t a, size_t b) {
             for (size_t i = a; i < b; ++i) {
                 const Block &bl = blocks[i];
-                const uint8_t *src = comp.data() + (bl.file_off - lo);
+                const uint8_t *src = map + bl.file_off;
                 const int xlen = rd16(src + 10);
                 const int hdr = 12 + xlen;
                 out[i].resize((size_t)bl.usize);
@@ -168,7 +163,8 @@ namespace {
 struct Stream {
     ncb_bam *bam;
     int64_t next_off;                 // file offset of the next block to load
-    static const int WINDOW = 128;    // blocks inflated per refill (<= 8 MB of text)
+    static const int WINDOW = 128;    // most blocks inflated per refill (<= 8 MB of text)
+    int window = 2;                   // grows geometrically: a short run inflates little past its end
     std::vector<Block> blocks;
     std::vector<std::vector<uint8_t>> data;
     size_t cur = 0;                   // current block of the window
@@ -185,13 +181,14 @@ struct Stream {
         cur = 0;
         pos = 0;
         Block bl;
-        while ((int)blocks.size() < WINDOW && next_off < bam->file_size) {
+        while ((int)blocks.size() < window && next_off < bam->file_size) {
             if (!bam->block_at(next_off, bl)) { failed = true; return false; }
             blocks.push_back(bl);
             next_off += bl.csize;
         }
         if (blocks.empty()) return false;
         if (!bam->inflate_blocks(blocks, data)) { failed = true; return false; }
+        window = window * 2 < WINDOW ? window * 2 : WINDOW;
         return true;
     }
     // virtual offset of the next byte: skips exhausted blocks first
@@ -354,13 +351,24 @@ int ncb_bam_open(ncb_bam **out, const char *path, int threads) {
     if (!b) return NCB_ERR_NOMEM;
     b->path = path;
     b->threads = threads < 1 ? 1 : threads;
-    b->f = fopen(path, "rb");
-    if (!b->f) {
+    const int fd = open(path, O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) {
+        if (fd >= 0) close(fd);
         delete b;
         return NCB_ERR_INVALID;
     }
-    fseeko(b->f, 0, SEEK_END);
-    b->file_size = ftello(b->f);
+    b->file_size = (int64_t)st.st_size;
+    if (b->file_size > 0) {
+        void *m = mmap(nullptr, (size_t)b->file_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) {
+            close(fd);
+            delete b;
+            return NCB_ERR_NOMEM;
+        }
+        b->map = (const uint8_t *)m;
+    }
+    close(fd);
     *out = b;   // returned even on a parse failure so that the caller can read the message
     if (!build_index(b)) {
         if (b->error.empty()) b->error = "cannot parse BAM";
@@ -371,7 +379,7 @@ int ncb_bam_open(ncb_bam **out, const char *path, int threads) {
 
 void ncb_bam_close(ncb_bam *b) {
     if (!b) return;
-    if (b->f) fclose(b->f);
+    if (b->map) munmap(const_cast<uint8_t *>(b->map), (size_t)b->file_size);
     delete b;
 }
 
