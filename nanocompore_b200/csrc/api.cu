@@ -28,7 +28,7 @@ struct ncb_handle {
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
     DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n, zbuf3, gmm_n3;
     DevBuf wl_count, wl_list;
-    DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch;
+    DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch, kw_rtab;
     DevBuf fdr_scratch, fdr_p, fdr_q;
     DevBuf unit_a, unit_b, unit_c, unit_d;
 };
@@ -147,6 +147,14 @@ int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
         delete h;
         return NCB_ERR_CUDA;
     }
+    // table of reciprocals for the exact-KS kernels, filled once
+    if (ensure(h, h->kw_rtab, NCB_KS_RTAB_SIZE * sizeof(double)) != NCB_OK ||
+        ncb_launch_ks_rtab((double *)h->kw_rtab.ptr, nullptr) < 0 || cudaDeviceSynchronize() != cudaSuccess) {
+        fprintf(stderr, "libncb: cannot set up device %d (%s)\n", device, cudaGetErrorString(cudaGetLastError()));
+        release(h->kw_rtab);
+        delete h;
+        return NCB_ERR_CUDA;
+    }
     const char *t = getenv("NCB_TIMING");
     h->timing = (t && t[0] == '1') ? 1 : 0;
     *out = h;
@@ -167,7 +175,7 @@ void ncb_destroy(ncb_handle *h) {
     DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
                      &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
                      &h->ks_h, &h->zbuf, &h->gmm_n, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
-                     &h->kw_bin, &h->kw_fetch, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
+                     &h->kw_bin, &h->kw_fetch, &h->kw_rtab, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : h->ev_log) cudaEventDestroy(e);
@@ -187,6 +195,7 @@ static int ks_work(ncb_handle *h, int64_t nprob, NcbKsWork &w) {
     w.list = (int32_t *)h->kw_list.ptr;
     w.bin = (uint8_t *)h->kw_bin.ptr;
     w.fetch = (int32_t *)h->kw_fetch.ptr;
+    w.rtab = (const double *)h->kw_rtab.ptr;   // filled by ncb_create
     return NCB_OK;
 }
 

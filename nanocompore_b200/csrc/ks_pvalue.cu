@@ -208,6 +208,14 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
     p_out[q] = clip01(result);
 }
 
+// correctly rounded reciprocals of the integers, once per handle: the wavefront kernel takes
+// 1 / (i + j) from here (L1-resident, loaded a step ahead) instead of computing it on the
+// critical path of every step
+__global__ void ks_rtab_kernel(double *rtab) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < NCB_KS_RTAB_SIZE; b += gridDim.x * blockDim.x)
+        rtab[b] = b ? __drcp_rn((double)b) : 0.0;
+}
+
 // ---- thread per problem: equal sizes -----------------------------------------------------
 __global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_out, NcbKsWork w) {
     const int lo = w.hist[NCB_KS_KIND_EQUAL * NCB_KS_BUCKETS];
@@ -270,10 +278,15 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
             int j = jlo - lane;
             double dj = (double)j;
             double den = (double)(i0 + jlo);
+            // i + j = i0 + jlo + t on every lane: one reciprocal per step for the warp, read from
+            // the table one step ahead of its use
+            // (the unit entry point accepts samples beyond the table: those divisors are inverted here)
+            auto recip = [&](int k) { return k < NCB_KS_RTAB_SIZE ? __ldg(w.rtab + k) : __drcp_rn((double)k); };
+            const int k0 = i0 + jlo;
+            double rden = recip(k0);
 #pragma unroll 1
             for (int t = 0; t < nsteps; ++t) {
-                // i + j = i0 + jlo + t on every lane: one reciprocal per step for the warp
-                const double rden = __drcp_rn(den);
+                const double rden_next = recip(k0 + t + 1);
                 const double up_sh = __shfl_up_sync(0xffffffffu, cur, 1);
                 if (row_on && j >= jlo && j < jhi) {
                     const double up = (lane == 0) ? prev[j & MASK] : up_sh;
@@ -288,6 +301,7 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
                 ++j;
                 dj += 1.0;
                 den += 1.0;
+                rden = rden_next;
             }
             __syncwarp();
         }
@@ -317,6 +331,11 @@ int ncb_configure_ks_kernels(void) {
                              KS_HUGE_WARPS * KS_HUGE_BUF * (int)sizeof(double));
     if (e != cudaSuccess) return -1;
     return 0;
+}
+
+int ncb_launch_ks_rtab(double *rtab, cudaStream_t s) {
+    ks_rtab_kernel<<<(NCB_KS_RTAB_SIZE + 255) / 256, 256, 0, s>>>(rtab);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, const int64_t *h,

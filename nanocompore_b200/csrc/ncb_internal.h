@@ -67,7 +67,10 @@ enum { NCB_KS_KIND_SMALL = 0,  /* unequal sizes, DP window <= NCB_KS_SMALL_WINDO
 #define NCB_KS_RING_FULL (NCB_MAX_READS / 2 + 1)   /* the HUGE kind holds the whole row: no wrap */
 #define NCB_KS_NBINS (NCB_KS_KINDS * NCB_KS_BUCKETS)
 
+#define NCB_KS_RTAB_SIZE (NCB_MAX_READS + 64)   /* reciprocals of i + j <= n0 + n1 <= NCB_MAX_READS */
+
 struct NcbKsWork {
+    const double *rtab; // [NCB_KS_RTAB_SIZE] correctly rounded reciprocals of the integers (per handle)
     int32_t *hist;      // [NCB_KS_NBINS + 1] counts -> exclusive offsets after the scan
     int32_t *cursor;    // [NCB_KS_NBINS]
     int32_t *list;      // [n_problems]
@@ -83,6 +86,8 @@ int ncb_launch_position_kernels(const NcbDeviceArgs &a, const NcbWorklists &w, i
 int ncb_launch_ks_pvalues(int64_t n_problems, const int32_t *n0, const int32_t *n1,
                           const int64_t *h, double *p_out, const NcbKsWork &w, int sm_count,
                           cudaStream_t s);
+// fills the handle's table of reciprocals (once, at ncb_create)
+int ncb_launch_ks_rtab(double *rtab, cudaStream_t s);
 int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, void *scratch,
                       size_t scratch_bytes, cudaStream_t s);
 size_t ncb_bh_fdr_scratch_bytes(int64_t n);
