@@ -168,15 +168,25 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
     double *A = A_all + threadIdx.x;
 #define AT(j) A[(j) * KS_SMALL_THREADS]
     const int n = k.n, m = k.m;
-    const long long mg = k.mg, ng = k.ng, hh = k.h;
-    int minj = 0, maxj = (int)min(ceildiv_ll(hh, mg), (long long)n + 1);
+    // every quantity fits in 32 bits (n0 + n1 < KS_RECIP_TABLE here)
+    const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
+    int minj = 0, maxj = min((hh + mg - 1) / mg, n + 1);
     int curlen = maxj - minj;
     for (int j = 0; j < NCB_KS_SMALL_WINDOW; ++j) AT(j) = (j < maxj) ? 0.0 : 1.0;
+    // band of row i: minj = floor((ng i - h) / mg) + 1 and maxj = ceil((ng i + h) / mg), clamped.
+    // Both numerators grow by ng <= mg per row, so the quotients advance by 0 or 1: they are
+    // carried as (quotient, remainder) pairs -- no division in the row loop.
+    int q_lo = -((hh + mg - 1) / mg), r_lo = q_lo * -mg - hh;          // floor(-h / mg), remainder in [0, mg)
+    int q_hi = (hh + mg - 1) / mg, r_hi = (hh + mg - 1) - q_hi * mg;   // floor((h + mg - 1) / mg)
     double result = -1.0;
     for (int i = 1; i <= m; ++i) {
         const int lastminj = minj, lastlen = curlen;
-        minj = (int)min(max(floordiv_ll(ng * i - hh, mg) + 1, 0LL), (long long)n);
-        maxj = (int)min(ceildiv_ll(ng * i + hh, mg), (long long)n + 1);
+        r_lo += ng;
+        if (r_lo >= mg) { r_lo -= mg; ++q_lo; }
+        r_hi += ng;
+        if (r_hi >= mg) { r_hi -= mg; ++q_hi; }
+        minj = min(max(q_lo + 1, 0), n);
+        maxj = min(q_hi, n + 1);
         if (maxj <= minj) { result = 1.0; break; }
         double val = (minj == 0) ? 0.0 : 1.0;
         const double di = (double)i;
