@@ -18,10 +18,12 @@
 //   SMALL  window <= 64 cells: one thread per problem, its window in shared memory
 //          (interleaved by thread: conflict free); a warp holds problems of one cost bucket
 //   EQUAL  one thread per problem
-//   LARGE / HUGE  one warp per problem: 32 rows advance together as a skewed wavefront
-//          (lane l is one column behind lane l-1 and takes the cell above by shuffle); the
-//          row above the 32-row chunk lives in shared memory.  Warps fetch problems from a
-//          counter, most expensive bucket first.
+//   LARGE  one warp per problem: 32 rows advance together as a skewed wavefront (lane l is one
+//          column behind lane l-1 and takes the cell above by shuffle); the row above the
+//          32-row chunk lives in a shared-memory ring.  Warps fetch problems from a counter,
+//          most expensive bucket first.
+//   HUGE   (>= 2^19 band cells, or a band too wide for the ring) one CTA per problem: 256 rows
+//          advance in lockstep, one barrier per step.
 #include "ncb_internal.h"
 #include "ncb_math.cuh"
 
@@ -37,6 +39,7 @@ __device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   //
 }
 
 #define KS_RECIP_TABLE 1024    /* reciprocals of i + j: SMALL problems have n0 + n1 < this */
+#define KS_CTA_MIN_CELLS 524288.0   /* band cells from which a problem gets a whole CTA (HUGE kind) */
 
 struct KsProblem {
     int m, n;            // m >= n
@@ -97,7 +100,8 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
                 double span = width + 2.0 * (32.0 * (double)k.ng / (double)k.mg) + 8.0;
                 int kind;
                 if (lenA <= NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) kind = NCB_KS_KIND_SMALL;
-                else if (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL) kind = NCB_KS_KIND_LARGE;
+                else if ((double)k.m * width < KS_CTA_MIN_CELLS &&
+                         (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL)) kind = NCB_KS_KIND_LARGE;
                 else kind = NCB_KS_KIND_HUGE;
                 bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
             }
@@ -320,12 +324,89 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
     }
 }
 
+// ---- CTA per problem: lockstep wavefront over THREADS rows ----------------------------------
+// The problems with the most band cells (a high-coverage position with a moderate shift: up to
+// 2 x 10^7 cells) would keep one warp busy for tens of milliseconds after everything else is
+// done.  Here THREADS rows advance together, thread r one column behind thread r - 1; the cell
+// above travels through a double-buffered shared-memory row (one barrier per step), the row
+// above the THREADS-row chunk is the full row `prev` (no wrap, so it never needs resetting: the
+// slots right of the band still hold the 1.0 of the initial fill).  Same cell arithmetic as the
+// other kernels, hence the same bits.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+ks_cta_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out, NcbKsWork w, int kind) {
+    extern __shared__ double cta_smem[];   // prev[NCB_KS_RING_FULL], xbuf[2][THREADS]
+    double *prev = cta_smem;
+    double *xbuf = cta_smem + NCB_KS_RING_FULL;
+    __shared__ int s_idx;
+    const int tid = threadIdx.x;
+    const int lo = w.hist[kind * NCB_KS_BUCKETS];
+    const int hi = w.hist[(kind + 1) * NCB_KS_BUCKETS];
+    for (;;) {
+        if (tid == 0) s_idx = lo + atomicAdd(&w.fetch[kind], 1);
+        __syncthreads();
+        const int idx = s_idx;
+        if (idx >= hi) break;
+        const int q = w.list[idx];
+        const KsProblem k = make_problem(n0[q], n1[q], h[q]);
+        const int n = k.n, m = k.m;
+        const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
+        const int maxj0 = min((hh + mg - 1) / mg, n + 1);
+        for (int j = tid; j <= n; j += THREADS) prev[j] = (j < maxj0) ? 0.0 : 1.0;
+        __syncthreads();
+        for (int i0 = 1; i0 <= m; i0 += THREADS) {
+            const int rows = min(THREADS, m - i0 + 1);
+            const int ilast = i0 + rows - 1;
+            const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
+            const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);
+            const int jhi = min((ng * ilast + hh + mg - 1) / mg, n + 1);
+            const int i = i0 + tid;
+            const bool row_on = tid < rows;
+            const double di = (double)i;
+            const int ngi = ng * i;
+            double left = 1.0, cur = 1.0;
+            const int nsteps = (jhi - jlo) + rows - 1;
+            int j = jlo - tid;
+            double dj = (double)j;
+            double den = (double)(i0 + jlo);
+            auto recip = [&](int kk) { return kk < NCB_KS_RTAB_SIZE ? __ldg(w.rtab + kk) : __drcp_rn((double)kk); };
+            const int k0 = i0 + jlo;
+            double rden = recip(k0);
+#pragma unroll 1
+            for (int t = 0; t < nsteps; ++t) {
+                const double rden_next = recip(k0 + t + 1);
+                double *xb = xbuf + (t & 1) * THREADS;
+                xb[tid] = cur;              // the cell this row finished in the step before
+                __syncthreads();
+                if (row_on && j >= jlo && j < jhi) {
+                    const double up = (tid == 0) ? prev[j] : xb[tid - 1];
+                    const int v = ngi - mg * j;
+                    double val = 1.0;
+                    if (abs(v) < hh)
+                        val = div_by_recip(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, dj)), den, rden);
+                    cur = val;
+                    left = val;
+                    if (tid == rows - 1) prev[j] = val;
+                }
+                ++j;
+                dj += 1.0;
+                den += 1.0;
+                rden = rden_next;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) p_out[q] = clip01(prev[n]);
+        __syncthreads();   // s_idx and prev are rewritten by the next problem
+    }
+}
+
 }  // namespace ncb
 
 using namespace ncb;
 
 static const int KS_LARGE_WARPS = 8, KS_LARGE_BUF = NCB_KS_RING_SMALL;
-static const int KS_HUGE_WARPS = 5, KS_HUGE_BUF = NCB_KS_RING_FULL;
+static const int KS_CTA_THREADS = 256;
+static const size_t KS_CTA_SMEM = (NCB_KS_RING_FULL + 2 * KS_CTA_THREADS) * sizeof(double);
 
 int ncb_configure_ks_kernels(void) {
     cudaError_t e;
@@ -336,9 +417,8 @@ int ncb_configure_ks_kernels(void) {
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                              KS_LARGE_WARPS * KS_LARGE_BUF * (int)sizeof(double));
     if (e != cudaSuccess) return -1;
-    e = cudaFuncSetAttribute(ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             KS_HUGE_WARPS * KS_HUGE_BUF * (int)sizeof(double));
+    e = cudaFuncSetAttribute(ks_cta_kernel<KS_CTA_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)KS_CTA_SMEM);
     if (e != cudaSuccess) return -1;
     return 0;
 }
@@ -358,9 +438,8 @@ int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, c
     ks_scan_kernel<<<1, NCB_KS_NBINS, 0, s>>>(w);
     ks_scatter_kernel<<<blocks, 256, 0, s>>>(nprob, w);
     // the long problems first: their warps are busy while the short kernels fill the rest
-    ks_warp_kernel<KS_HUGE_WARPS, KS_HUGE_BUF, false>
-        <<<sm_count, KS_HUGE_WARPS * 32, KS_HUGE_WARPS * KS_HUGE_BUF * sizeof(double), s>>>(
-            n0, n1, h, p_out, w, NCB_KS_KIND_HUGE);
+    ks_cta_kernel<KS_CTA_THREADS><<<sm_count * 4, KS_CTA_THREADS, KS_CTA_SMEM, s>>>(
+        n0, n1, h, p_out, w, NCB_KS_KIND_HUGE);
     ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF, true>
         <<<sm_count * 3, KS_LARGE_WARPS * 32, KS_LARGE_WARPS * KS_LARGE_BUF * sizeof(double), s>>>(
             n0, n1, h, p_out, w, NCB_KS_KIND_LARGE);

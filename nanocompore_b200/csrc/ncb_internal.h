@@ -60,7 +60,8 @@ struct NcbWorklists {
 enum { NCB_KS_KIND_SMALL = 0,  /* unequal sizes, DP window <= NCB_KS_SMALL_WINDOW: thread per problem */
        NCB_KS_KIND_EQUAL = 1,  /* equal sizes: Horner product, thread per problem        */
        NCB_KS_KIND_LARGE = 2,  /* unequal sizes, band span <= 1024 columns: warp wavefront, 8 KB ring */
-       NCB_KS_KIND_HUGE = 3,   /* unequal sizes, wider band: warp wavefront, full row (41 KB) per warp */
+       NCB_KS_KIND_HUGE = 3,   /* unequal sizes, wider band or >= 2^19 band cells: CTA lockstep wavefront
+                                  over 256 rows, full row (41 KB) per CTA */
        NCB_KS_KINDS = 4 };
 #define NCB_KS_SMALL_WINDOW 64
 #define NCB_KS_RING_SMALL 1024   /* doubles in the ring of the LARGE kind */

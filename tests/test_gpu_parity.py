@@ -198,6 +198,30 @@ def test_ks_exact_pvalue_unit(engine_factory):
     assert (got == want).mean() > 0.99
 
 
+def test_ks_exact_pvalue_cta_class(engine_factory):
+    """The CTA-per-problem wavefront (problems of >= 2^19 band cells): bitwise SciPy's compiled
+    lattice recurrence, chunk edges included (m a multiple of 256, one row left over, n = 1 ...)."""
+    from scipy.stats._stats_py import _compute_outer_prob_inside_method
+    eng = engine_factory(tests=('KS',))
+    shapes = [(5000, 4999, 0.05), (5120, 5119, 0.02), (4100, 257, 0.4), (3000, 2048, 0.1), (5121, 5000, 0.03),
+              (4097, 4096, 0.06), (2305, 2304, 0.12), (5000, 4861, 0.3), (4608, 3001, 0.08), (10000, 240, 0.5),
+              (5120, 1300, 0.2), (3329, 3328, 0.2)]
+    n0 = np.array([a for a, _, _ in shapes], dtype=np.int32)
+    n1 = np.array([b for _, b, _ in shapes], dtype=np.int32)
+    n0[::2], n1[::2] = n1[::2].copy(), n0[::2].copy()        # either sample may be the larger one
+    g = np.gcd(n0, n1)
+    lcm = n0.astype(np.int64) // g * n1
+    h = np.array([max(1, round(d * l)) for (_, _, d), l in zip(shapes, lcm)], dtype=np.int64)
+    m, n = np.maximum(n0, n1), np.minimum(n0, n1)
+    cells = m * np.minimum(2.0 * h / (m // g) + 1, n + 1)
+    assert (cells >= 2 ** 19).all()
+    got = eng.ks_exact_pvalues(n0, n1, h)
+    want = np.array([min(max(_compute_outer_prob_inside_method(int(a), int(b), int(c), int(d)), 0.0), 1.0)
+                     for a, b, c, d in zip(n0, n1, g, h)])
+    assert (want > 0).sum() >= 8                            # not only underflowed tails
+    assert np.array_equal(got, want)
+
+
 def test_bh_fdr_unit(engine_factory):
     from oracle.fdr import multipletests_filter_nan
     eng = engine_factory(tests=('KS',))
