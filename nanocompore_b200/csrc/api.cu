@@ -521,7 +521,7 @@ int ncb_probe_fp64_peak(ncb_handle *h, double *tflops, void *stream) {
     CK(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     ENSURE(h->unit_a, 256);
-    const int iters = 1 << 16, blocks = h->sm_count * 8, threads = 256;
+    const int iters = 1 << 13, blocks = h->sm_count * 8, threads = 256;   // ~1 ms per repetition
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));

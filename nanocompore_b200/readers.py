@@ -371,14 +371,10 @@ class TranscriptPipeline:
         return select_reads(rows, self._conf.get_downsample_high_coverage(),
                             self._conf.get_min_coverage(), offset)
 
-    def run(self, transcripts):
-        """Returns ``[(transcript, DataFrame | None)]``; ``None`` = no reads or no tested position
-        (run.py:428-456).  The frame carries the ``kmer`` column of run.py:461-463 when the
-        transcript has a sequence."""
-        conf = self._conf
-        offset = conf.get_motor_dwell_offset()
-        min_cov = conf.get_min_coverage()
-        out = [(t, None) for t in transcripts]
+    def prepare(self, transcripts):
+        """Host half of a batch: read, select, pack into one pinned CSR batch (no GPU work; the
+        native calls release the GIL, so this overlaps the kernels of the batch before)."""
+        offset = self._conf.get_motor_dwell_offset()
         live, row_sets, masks = [], [], []
         for i, t in enumerate(transcripts):
             rows, keep = self.read(t)
@@ -387,9 +383,18 @@ class TranscriptPipeline:
             live.append(i)
             row_sets.append(rows)
             masks.append(keep)
+        packed = pack_rows(row_sets, offset, pin=True) if live else None
+        return transcripts, live, row_sets, masks, packed
+
+    def finish(self, prepared):
+        """Device half: one ``ncb_compare`` for the batch and the result frames."""
+        transcripts, live, row_sets, masks, packed = prepared
+        conf = self._conf
+        min_cov = conf.get_min_coverage()
+        out = [(t, None) for t in transcripts]
         if not live:
             return out
-        batch, ptx, pidx = pack_rows(row_sets, offset, pin=True)
+        batch, ptx, pidx = packed
         # a position is tested when it has a valid intensity (run.py:587) and enough coverage in
         # both conditions (run.py:511-515): the statistics kernel applies both (min_coverage >= 1);
         # after a downsample the reference keeps the positions chosen BEFORE it, so the host mask
@@ -421,3 +426,23 @@ class TranscriptPipeline:
                 frame['kmer'] = [encode_kmer(seq[p:p + klen]) for p in frame.pos]   # run.py:461-463
             out[i] = (t, frame)
         return out
+
+    def run(self, transcripts):
+        """Returns ``[(transcript, DataFrame | None)]``; ``None`` = no reads or no tested position
+        (run.py:428-456).  The frame carries the ``kmer`` column of run.py:461-463 when the
+        transcript has a sequence."""
+        return self.finish(self.prepare(transcripts))
+
+    def run_stream(self, transcripts, batch_size=32):
+        """Generator over ``run`` results for a long list of transcripts, ``batch_size`` at a time:
+        a host thread reads and packs batch k + 1 while the GPU works on batch k and its frames are
+        assembled (the task queue of run.py:104-131 and 380-420, as a two-stage pipeline)."""
+        batches = [transcripts[i:i + batch_size] for i in range(0, len(transcripts), batch_size)]
+        if not batches:
+            return
+        with ThreadPoolExecutor(max_workers=1) as ex:
+            pending = ex.submit(self.prepare, batches[0])
+            for nxt in batches[1:] + [None]:
+                prepared = pending.result()
+                pending = ex.submit(self.prepare, nxt) if nxt is not None else None
+                yield from self.finish(prepared)

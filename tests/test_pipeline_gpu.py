@@ -157,6 +157,14 @@ def test_files_to_frames(tmp_path, kind):
         assert list(df['kmer']) == [R.encode_kmer(t.seq[p:p + 5]) for p in df['pos']]
         tested += len(df)
     assert tested > 200
+    # the two-stage pipeline (read/pack of the next batch under the kernels of this one) gives
+    # the same frames, in order
+    streamed = list(pipe.run_stream(transcripts, batch_size=1))
+    assert [t.name for t, _ in streamed] == [t.name for t in transcripts]
+    for (_, a), (_, b) in zip(streamed, out):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.equals(b)
     reader.close()
 
 
