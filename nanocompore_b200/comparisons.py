@@ -180,17 +180,15 @@ class TranscriptComparator:
 
     def _assemble(self, transcript, positions, status, pv, st, counts, with_motor):
         """Result frame of one transcript from its slice of the result columns
-        (comparisons.py:83-84, 108-148, 204-215)."""
+        (comparisons.py:83-84, 108-148, 204-215).  Without the ``auto`` method every test covers
+        every row, and the frame is built once from a dict of columns (inserting ~25 columns one
+        by one costs more than the kernels of the transcript); with ``auto`` the reference's
+        incremental merge is followed step by step."""
         pos_host = positions.cpu() if isinstance(positions, torch.Tensor) else torch.as_tensor(positions)
-        results = pd.DataFrame({'transcript_id': transcript.id, 'pos': pos_host})
         if (status & L.NCB_POS_TOO_MANY_READS).any():
             raise NanocomporeError(
                 f"A position of transcript {transcript.name} has more than {L.NCB_MAX_READS} reads; "
                 "lower downsample_high_coverage")
-
-        for column, row in shift_columns(with_motor):
-            results[column] = st[row]
-
         # comparisons.py:108-120
         bad_stds = (status & L.NCB_POS_BAD_STD) != 0
         if bad_stds.any():
@@ -199,26 +197,39 @@ class TranscriptComparator:
                 "The standard deviation cannot be calculated for some positions on "
                 f"transcript {transcript.name}, but are required for scaling the data. "
                 f"The positions {pos_host[torch.from_numpy(bad_stds)].tolist()} will be skipped.")
-            results.drop(np.arange(results.shape[0])[bad_stds], inplace=True, axis=0)
         keep = ~bad_stds
         n_positions = int(keep.sum())
-        status, pv, st, counts = status[keep], pv[:, keep], st[:, keep], counts[:, :, keep]
-
         methods = list(self._config.get_comparison_methods())
-        has_auto = 'auto' in methods
-        auto_test_mask = None
-        if has_auto:
-            auto_test_mask = np.where((status & L.NCB_POS_AUTO_GMM) != 0, 'GMM', 'KS')
+        context = self._config.get_sequence_context()
+
+        if 'auto' not in methods:
+            pos = pos_host.numpy()[keep]
+            columns = {'transcript_id': np.full(n_positions, transcript.id), 'pos': pos}
+            for column, row in shift_columns(with_motor):
+                columns[column] = st[row][keep]
+            status, pv, st, counts = status[keep], pv[:, keep], st[:, keep], counts[:, :, keep]
+            for test in self._get_test_masks(None, n_positions):
+                columns.update(self._test_columns(test, pv, st, counts, status, transcript))
+            if context > 0:
+                for test in [col for col in columns if 'pvalue' in col]:
+                    columns[f"{test}_context_{context}"] = self._combine_context(pos, columns[test])
+            # the index keeps the row labels of the unfiltered frame, like the reference's drop()
+            return pd.DataFrame(columns, index=np.arange(keep.size)[keep])
+
+        results = pd.DataFrame({'transcript_id': transcript.id, 'pos': pos_host})
+        for column, row in shift_columns(with_motor):
+            results[column] = st[row]
+        if bad_stds.any():
+            results.drop(np.arange(results.shape[0])[bad_stds], inplace=True, axis=0)
+        status, pv, st, counts = status[keep], pv[:, keep], st[:, keep], counts[:, :, keep]
+        auto_test_mask = np.where((status & L.NCB_POS_AUTO_GMM) != 0, 'GMM', 'KS')
         for test, mask in self._get_test_masks(auto_test_mask, n_positions).items():
             test_results = self._test_columns(test, pv, st, counts, status, transcript)
             self._merge_results(results, test_results, test, mask, auto_test_mask, n_positions)
-
-        context = self._config.get_sequence_context()
         if context > 0:
             tests = [col for col in results.columns if 'pvalue' in col]
             for test in tests:
                 results[f"{test}_context_{context}"] = self._combine_context_pvalues(results, test)
-
         return results
 
     def _get_test_masks(self, auto_test_mask, n_positions):
@@ -277,6 +288,9 @@ class TranscriptComparator:
                 results.loc[rows, 'auto_pvalue'] = results.loc[rows, column]
 
     def _combine_context_pvalues(self, results, test):
+        return self._combine_context(results.pos.to_numpy(), results[test].to_numpy(dtype=float))
+
+    def _combine_context(self, pos, pvalues):
         # comparisons.py:436-474 (host side).  Same arithmetic as the reference's
         # per-window combine_pvalues_hou, evaluated for all windows of the transcript at once.
         context = self._config.get_sequence_context()
@@ -284,10 +298,10 @@ class TranscriptComparator:
             weights = harmomic_series(context)
         else:
             weights = [1] * (2 * context + 1)
-        pos = results.pos.to_numpy().astype(np.int64)
+        pos = np.asarray(pos).astype(np.int64)
         idx = pos - pos.min()
         padded = np.ones(int(idx.max()) + 1 + 2 * context, dtype=float)
-        padded[idx + context] = results[test].to_numpy(dtype=float)
+        padded[idx + context] = np.asarray(pvalues, dtype=float)
         corr = cross_corr_matrix(padded[context:-context], context)
         windows = np.lib.stride_tricks.sliding_window_view(padded, 2 * context + 1)
         return combine_windows_hou(windows, weights, corr, context)[idx]

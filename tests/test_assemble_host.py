@@ -1,0 +1,99 @@
+"""Host logic of the drop-in comparator: the result frame built from libncb's result columns
+(comparisons.py:83-84, 108-148, 204-215 of the reference).  No GPU: the columns are made up."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from nanocompore_b200 import _lib as L
+from nanocompore_b200.comparisons import SHIFT_COLUMNS, TranscriptComparator
+from nanocompore_b200.config import PathConfig
+
+DATA = {'kd': {'kd1': {}, 'kd2': {}}, 'wt': {'wt1': {}, 'wt2': {}}}
+
+
+class Worker:
+    def __init__(self):
+        self.messages = []
+
+    def log(self, level, msg):
+        self.messages.append((level, msg))
+
+
+class Transcript:
+    id, name = 7, 'tx'
+
+
+def columns(P, rng, bad=(), auto_gmm=()):
+    status = np.zeros(P, np.int32)
+    status[list(bad)] |= L.NCB_POS_BAD_STD
+    status[list(auto_gmm)] |= L.NCB_POS_AUTO_GMM
+    pv = rng.random((L.NCB_PV_ROWS, P))
+    st = rng.random((L.NCB_ST_ROWS, P)).astype(np.float32)
+    counts = rng.integers(0, 50, (4, 2, P)).astype(np.int32)
+    return status, pv, st, counts
+
+
+def test_frame_layout_and_dropped_rows():
+    rng = np.random.default_rng(1)
+    P = 40
+    status, pv, st, counts = columns(P, rng, bad=(3, 17))
+    worker = Worker()
+    cfg = PathConfig(dict(data=DATA, depleted_condition='kd', comparison_methods=['GMM', 'KS', 'MW']))
+    df = TranscriptComparator(cfg, worker)._assemble(Transcript, torch.arange(100, 100 + P, dtype=torch.int16),
+                                                     status, pv, st, counts, False)
+    keep = np.ones(P, bool)
+    keep[[3, 17]] = False
+    assert list(df.columns[:2]) == ['transcript_id', 'pos'] and list(df.columns[2:14]) == [c for c, _ in SHIFT_COLUMNS]
+    assert list(df.columns[14:]) == ['GMM_chi2_pvalue', 'GMM_LOR', 'kd1_mod', 'kd1_unmod', 'kd2_mod', 'kd2_unmod',
+                                     'wt1_mod', 'wt1_unmod', 'wt2_mod', 'wt2_unmod', 'KS_intensity_pvalue',
+                                     'KS_dwell_pvalue', 'MW_intensity_pvalue', 'MW_dwell_pvalue']
+    # rows with an undefined standard deviation are dropped with a warning; labels keep their gaps
+    assert list(df.index) == list(np.arange(P)[keep]) and (df['transcript_id'] == 7).all()
+    np.testing.assert_array_equal(df['pos'].to_numpy(), np.arange(100, 100 + P)[keep])
+    assert any(level == 'warning' and '[103, 117]' in msg for level, msg in worker.messages)
+    np.testing.assert_array_equal(df['KS_dwell_pvalue'].to_numpy(), pv[L.PV['KS_DWELL']][keep])
+    np.testing.assert_array_equal(df['GMM_LOR'].to_numpy(), st[L.ST['GMM_LOR']][keep])
+    np.testing.assert_array_equal(df['wt1_unmod'].to_numpy(), counts[2, 1][keep].astype(np.uint32))
+    assert df['kd1_mod'].dtype == np.uint32 and df['GMM_LOR'].dtype == np.float32 and df['pos'].dtype == np.int16
+
+
+def test_auto_routing_columns():
+    """comparisons.py:150-215: with 'auto' every row gets the p-value of its automatic test."""
+    rng = np.random.default_rng(2)
+    P = 30
+    gmm_rows = (2, 3, 11, 29)
+    status, pv, st, counts = columns(P, rng, auto_gmm=gmm_rows)
+    cfg = PathConfig(dict(data=DATA, depleted_condition='kd', comparison_methods=['auto']))
+    df = TranscriptComparator(cfg, Worker())._assemble(Transcript, torch.arange(P, dtype=torch.int16),
+                                                       status, pv, st, counts, False)
+    is_gmm = np.zeros(P, bool)
+    is_gmm[list(gmm_rows)] = True
+    assert list(df['auto_test']) == ['GMM' if g else 'KS' for g in is_gmm]
+    want = np.where(is_gmm, pv[L.PV['GMM_CHI2']], pv[L.PV['KS_INTENSITY']])
+    np.testing.assert_array_equal(df['auto_pvalue'].to_numpy(), want)
+    assert df['KS_intensity_pvalue'][is_gmm].isna().all() and df['GMM_chi2_pvalue'][~is_gmm].isna().all()
+
+
+def test_context_columns_follow_every_pvalue_column():
+    rng = np.random.default_rng(3)
+    P = 60
+    status, pv, st, counts = columns(P, rng)
+    cfg = PathConfig(dict(data=DATA, depleted_condition='kd', comparison_methods=['KS'], sequence_context=2))
+    df = TranscriptComparator(cfg, Worker())._assemble(Transcript, torch.arange(P, dtype=torch.int16),
+                                                       status, pv, st, counts, False)
+    assert list(df.columns[-2:]) == ['KS_intensity_pvalue_context_2', 'KS_dwell_pvalue_context_2']
+    from oracle.context import combine_context_pvalues
+    want = combine_context_pvalues(np.arange(P), pv[L.PV['KS_INTENSITY']], 2)
+    np.testing.assert_allclose(df['KS_intensity_pvalue_context_2'].to_numpy(), want, rtol=1e-12)
+
+
+def test_too_many_reads_raises():
+    from nanocompore_b200.comparisons import NanocomporeError
+    rng = np.random.default_rng(4)
+    status, pv, st, counts = columns(5, rng)
+    status[2] |= L.NCB_POS_TOO_MANY_READS
+    cfg = PathConfig(dict(data=DATA, depleted_condition='kd'))
+    with pytest.raises(NanocomporeError):
+        TranscriptComparator(cfg, Worker())._assemble(Transcript, torch.arange(5, dtype=torch.int16),
+                                                      status, pv, st, counts, False)
