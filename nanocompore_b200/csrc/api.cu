@@ -189,7 +189,7 @@ static int ks_work(ncb_handle *h, int64_t nprob, NcbKsWork &w) {
     ENSURE(h->kw_cursor, NCB_KS_NBINS * sizeof(int32_t));
     ENSURE(h->kw_list, (size_t)nprob * sizeof(int32_t));
     ENSURE(h->kw_bin, (size_t)nprob);
-    ENSURE(h->kw_fetch, NCB_KS_KINDS * sizeof(int32_t));
+    ENSURE(h->kw_fetch, (NCB_KS_KINDS + 1) * sizeof(int32_t));
     w.hist = (int32_t *)h->kw_hist.ptr;
     w.cursor = (int32_t *)h->kw_cursor.ptr;
     w.list = (int32_t *)h->kw_list.ptr;

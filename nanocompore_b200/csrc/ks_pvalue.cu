@@ -22,8 +22,8 @@
 //          column behind lane l-1 and takes the cell above by shuffle); the row above the
 //          32-row chunk lives in a shared-memory ring.  Warps fetch problems from a counter,
 //          most expensive bucket first.
-//   HUGE   (>= 2^19 band cells, or a band too wide for the ring) one CTA per problem: 256 rows
-//          advance in lockstep, one barrier per step.
+//   HUGE   (a band too wide for the ring, plus the LARGE problems that alone would outlast the
+//          batch) one CTA per problem: 256 rows advance in lockstep, one barrier per step.
 #include "ncb_internal.h"
 #include "ncb_math.cuh"
 
@@ -39,7 +39,11 @@ __device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   //
 }
 
 #define KS_RECIP_TABLE 1024    /* reciprocals of i + j: SMALL problems have n0 + n1 < this */
-#define KS_CTA_MIN_CELLS 524288.0   /* band cells from which a problem gets a whole CTA (HUGE kind) */
+/* A LARGE problem gets a whole CTA instead of a warp when it alone would outlast the batch: its
+ * band cells exceed 1/KS_CTA_SHARE of all wavefront cells of the batch (about the number of warps
+ * the wavefront kernel keeps resident), and at least KS_CTA_MIN_CELLS. */
+#define KS_CTA_SHARE 3072.0
+#define KS_CTA_MIN_CELLS 131072.0
 
 struct KsProblem {
     int m, n;            // m >= n
@@ -100,8 +104,7 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
                 double span = width + 2.0 * (32.0 * (double)k.ng / (double)k.mg) + 8.0;
                 int kind;
                 if (lenA <= NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) kind = NCB_KS_KIND_SMALL;
-                else if ((double)k.m * width < KS_CTA_MIN_CELLS &&
-                         (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL)) kind = NCB_KS_KIND_LARGE;
+                else if (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL) kind = NCB_KS_KIND_LARGE;
                 else kind = NCB_KS_KIND_HUGE;
                 bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
             }
@@ -111,12 +114,21 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
     }
 }
 
-// exclusive scan of the NCB_KS_NBINS counters (one block of NCB_KS_NBINS threads)
+// representative cost (band cells) of a bucket: the inverse of cost_bucket
+__device__ __forceinline__ double bucket_cost(int b) {
+    return exp2(0.5 * (double)(NCB_KS_BUCKETS - 1 - b) - 0.75);   // middle of [2^(b'/2 - 1), 2^(b'/2 - 1/2))
+}
+
+// exclusive scan of the NCB_KS_NBINS counters (one block of NCB_KS_NBINS threads), and the split of
+// the LARGE problems between the CTA kernel (the dearest ones, a prefix of their cost-sorted
+// list) and the warp kernel: w.fetch[NCB_KS_KINDS] = length of that prefix
 __global__ void ks_scan_kernel(NcbKsWork w) {
     __shared__ int s[NCB_KS_NBINS];
+    __shared__ int raw[NCB_KS_NBINS];
     int t = threadIdx.x;
     int v = w.hist[t];
     s[t] = v;
+    raw[t] = v;
     __syncthreads();
     for (int d = 1; d < NCB_KS_NBINS; d <<= 1) {
         int y = t >= d ? s[t - d] : 0;
@@ -129,6 +141,17 @@ __global__ void ks_scan_kernel(NcbKsWork w) {
     w.cursor[t] = excl;
     if (t == NCB_KS_NBINS - 1) w.hist[NCB_KS_NBINS] = s[t];
     if (t < NCB_KS_KINDS) w.fetch[t] = 0;
+    if (t == 0) {
+        double total = 0.0;
+        for (int b = 0; b < NCB_KS_BUCKETS; ++b)
+            total += bucket_cost(b) * (double)(raw[NCB_KS_KIND_LARGE * NCB_KS_BUCKETS + b] +
+                                               raw[NCB_KS_KIND_HUGE * NCB_KS_BUCKETS + b]);
+        const double cut = fmax(total / KS_CTA_SHARE, KS_CTA_MIN_CELLS);
+        int n_cut = 0;
+        for (int b = 0; b < NCB_KS_BUCKETS && bucket_cost(b) >= cut; ++b)
+            n_cut += raw[NCB_KS_KIND_LARGE * NCB_KS_BUCKETS + b];
+        w.fetch[NCB_KS_KINDS] = n_cut;
+    }
 }
 
 __global__ void ks_scatter_kernel(int64_t nprob, NcbKsWork w) {
@@ -255,7 +278,7 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
     double *prev = rows_all + (size_t)(threadIdx.x >> 5) * RING;
     constexpr int MASK = WRAP ? RING - 1 : -1;   // WRAP = false: RING > n, plain indexing
     static_assert(!WRAP || (RING & (RING - 1)) == 0, "ring size must be a power of two");
-    const int lo = w.hist[kind * NCB_KS_BUCKETS];
+    const int lo = w.hist[kind * NCB_KS_BUCKETS] + w.fetch[NCB_KS_KINDS];   // the dearest go to the CTA kernel
     const int hi = w.hist[(kind + 1) * NCB_KS_BUCKETS];
     for (;;) {
         int idx = 0;
@@ -327,7 +350,7 @@ ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
 // ---- CTA per problem: lockstep wavefront over THREADS rows ----------------------------------
 // The problems with the most band cells (a high-coverage position with a moderate shift: up to
 // 2 x 10^7 cells) would keep one warp busy for tens of milliseconds after everything else is
-// done.  Here THREADS rows advance together, thread r one column behind thread r - 1; the cell
+// done; ks_scan_kernel hands those to this kernel.  Here THREADS rows advance together, thread r one column behind thread r - 1; the cell
 // above travels through a double-buffered shared-memory row (one barrier per step), the row
 // above the THREADS-row chunk is the full row `prev` (no wrap, so it never needs resetting: the
 // slots right of the band still hold the 1.0 of the initial fill).  Same cell arithmetic as the
@@ -340,14 +363,17 @@ ks_cta_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_
     double *xbuf = cta_smem + NCB_KS_RING_FULL;
     __shared__ int s_idx;
     const int tid = threadIdx.x;
+    // its problems: the HUGE bins, then the dearest LARGE ones (a prefix of their sorted list)
     const int lo = w.hist[kind * NCB_KS_BUCKETS];
-    const int hi = w.hist[(kind + 1) * NCB_KS_BUCKETS];
+    const int n_own = w.hist[(kind + 1) * NCB_KS_BUCKETS] - lo;
+    const int lo_large = w.hist[NCB_KS_KIND_LARGE * NCB_KS_BUCKETS];
+    const int n_all = n_own + w.fetch[NCB_KS_KINDS];
     for (;;) {
-        if (tid == 0) s_idx = lo + atomicAdd(&w.fetch[kind], 1);
+        if (tid == 0) s_idx = atomicAdd(&w.fetch[kind], 1);
         __syncthreads();
         const int idx = s_idx;
-        if (idx >= hi) break;
-        const int q = w.list[idx];
+        if (idx >= n_all) break;
+        const int q = w.list[idx < n_own ? lo + idx : lo_large + (idx - n_own)];
         const KsProblem k = make_problem(n0[q], n1[q], h[q]);
         const int n = k.n, m = k.m;
         const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;

@@ -60,8 +60,8 @@ struct NcbWorklists {
 enum { NCB_KS_KIND_SMALL = 0,  /* unequal sizes, DP window <= NCB_KS_SMALL_WINDOW: thread per problem */
        NCB_KS_KIND_EQUAL = 1,  /* equal sizes: Horner product, thread per problem        */
        NCB_KS_KIND_LARGE = 2,  /* unequal sizes, band span <= 1024 columns: warp wavefront, 8 KB ring */
-       NCB_KS_KIND_HUGE = 3,   /* unequal sizes, wider band or >= 2^19 band cells: CTA lockstep wavefront
-                                  over 256 rows, full row (41 KB) per CTA */
+       NCB_KS_KIND_HUGE = 3,   /* unequal sizes, wider band: CTA lockstep wavefront over 256 rows, full row
+                                  (41 KB) per CTA; it also takes the LARGE problems that would outlast the batch */
        NCB_KS_KINDS = 4 };
 #define NCB_KS_SMALL_WINDOW 64
 #define NCB_KS_RING_SMALL 1024   /* doubles in the ring of the LARGE kind */
@@ -76,7 +76,8 @@ struct NcbKsWork {
     int32_t *cursor;    // [NCB_KS_NBINS]
     int32_t *list;      // [n_problems]
     uint8_t *bin;       // [n_problems] bin of each problem, 255 = answered directly
-    int32_t *fetch;     // [NCB_KS_KINDS] dynamic work counters of the warp kernels
+    int32_t *fetch;     // [NCB_KS_KINDS] dynamic work counters of the wavefront kernels;
+                        // [NCB_KS_KINDS]: LARGE problems taken over by the CTA kernel
 };
 
 // launchers (each returns the number of kernels launched, or <0 on launch error)

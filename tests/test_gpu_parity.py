@@ -199,7 +199,7 @@ def test_ks_exact_pvalue_unit(engine_factory):
 
 
 def test_ks_exact_pvalue_cta_class(engine_factory):
-    """The CTA-per-problem wavefront (problems of >= 2^19 band cells): bitwise SciPy's compiled
+    """The CTA-per-problem wavefront (the problems that get a whole CTA): bitwise SciPy's compiled
     lattice recurrence, chunk edges included (m a multiple of 256, one row left over, n = 1 ...)."""
     from scipy.stats._stats_py import _compute_outer_prob_inside_method
     eng = engine_factory(tests=('KS',))
