@@ -1,0 +1,72 @@
+"""Wide parity sweep (not part of the test-suite): many seeded transcripts through the CUDA path
+and through the oracle (a process pool on the host cores), every check of
+tests/test_gpu_parity.py:check_against_oracle per transcript.  Prints a JSON summary.
+
+    python tests/gpu_parity_sweep.py [n_transcripts] [positions] [processes]
+"""
+import json
+import os
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+SHAPES = [(40, False), (100, False), (100, True), (150, False), (31, True), (230, False), (12, True)]
+
+
+def gpu_results(jobs):
+    import torch
+    from nanocompore_b200.engine import Engine, make_labels
+    from oracle import prep as oprep
+    from nanocompore_b200.synthetic import make_transcript
+    eng = Engine(0, tests=('KS', 'MW', 'TT', 'GMM'), with_logit=True)
+    out = []
+    for seed, P, n, q in jobs:
+        tx = make_transcript(np.random.default_rng(seed), P, n, quantised=q)
+        data, samples, conditions, _ = oprep.prepare_data(tx.data, tx.samples, tx.conditions)
+        res = eng.compare_dense(torch.from_numpy(data).cuda(), torch.from_numpy(make_labels(samples, conditions)).cuda(),
+                                diagnostics=True).numpy()
+        out.append(res)
+    eng.close()
+    return out
+
+
+def check(args):
+    (seed, P, n, q), res = args
+    os.environ['CUDA_VISIBLE_DEVICES'] = ''
+    import test_gpu_parity as T
+    from nanocompore_b200.synthetic import make_transcript
+    from oracle import prep as oprep
+    tx = make_transcript(np.random.default_rng(seed), P, n, quantised=q)
+    data, samples, conditions, _ = oprep.prepare_data(tx.data, tx.samples, tx.conditions)
+    try:
+        ok = T.check_against_oracle(res, data, samples, conditions)
+        return seed, int(ok.sum()), None
+    except AssertionError as e:
+        return seed, 0, f"seed {seed} n {n} quantised {q}: {str(e)[:400]}"
+
+
+def main():
+    n_tx = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+    procs = int(sys.argv[3]) if len(sys.argv) > 3 else (os.cpu_count() or 1)
+    jobs = [(9000 + i, P) + SHAPES[i % len(SHAPES)] for i in range(n_tx)]
+    t0 = time.perf_counter()
+    res = gpu_results(jobs)
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=procs) as ex:
+        outcomes = list(ex.map(check, zip(jobs, res)))
+    failures = [msg for _, _, msg in outcomes if msg]
+    print(json.dumps(dict(transcripts=n_tx, positions_checked=sum(k for _, k, _ in outcomes), failures=len(failures),
+                          first_failures=failures[:5], gpu_s=t_gpu, oracle_s=time.perf_counter() - t0)), flush=True)
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == '__main__':
+    main()
