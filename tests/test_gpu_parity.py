@@ -283,3 +283,26 @@ def test_motor_dwell_three_variables(engine_factory, n, gap):
     n_fit = np.where(use3, valid.all(2).sum(1), (valid[:, :, 0] & valid[:, :, 1]).sum(1))
     cont = sum(res['diag_i64'][L.DI[f'CONT_{c}{k}']] for c in (0, 1) for k in (0, 1))[ok]
     assert_equal_nan(cont, n_fit, 'reads in the fit')
+
+
+def test_correct_pvalues_mirror(engine_factory):
+    """nanocompore_b200.postprocessing.correct_pvalues = Postprocessor._correct_pvalues
+    (postprocessing.py:209-252), auto_qvalue scaling included, against the oracle restatement."""
+    import pandas as pd
+    from nanocompore_b200.postprocessing import correct_pvalues
+    from oracle.fdr import auto_qvalues, multipletests_filter_nan
+    eng = engine_factory(tests=('KS',))
+    rng = np.random.default_rng(8)
+    n = 5000
+    df = pd.DataFrame({'pos': np.arange(n), 'KS_intensity_pvalue': rng.random(n) ** 3,
+                       'GMM_chi2_pvalue': rng.random(n) ** 2, 'auto_pvalue': rng.random(n) ** 4,
+                       'auto_test': np.where(rng.random(n) < 0.3, 'GMM', 'KS'), 'GMM_LOR': rng.random(n)})
+    for col in ('KS_intensity_pvalue', 'GMM_chi2_pvalue', 'auto_pvalue'):
+        df.loc[rng.random(n) < 0.1, col] = np.nan
+    want_auto = auto_qvalues(df['auto_pvalue'].to_numpy(), df['auto_test'].to_numpy())
+    want_ks = multipletests_filter_nan(df['KS_intensity_pvalue'].to_numpy())
+    out = correct_pvalues(eng, df.copy(), auto_test=df['auto_test'])
+    assert list(out.columns) == sorted(out.columns)
+    assert {'KS_intensity_qvalue', 'GMM_chi2_qvalue', 'auto_qvalue'} <= set(out.columns) and 'GMM_LOR' in out.columns
+    np.testing.assert_allclose(out['KS_intensity_qvalue'].to_numpy(), want_ks, rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(out['auto_qvalue'].to_numpy(), want_auto, rtol=1e-12, equal_nan=True)
