@@ -103,7 +103,9 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
                 // columns a 32-row chunk of the wavefront touches, plus those entering next
                 double span = width + 2.0 * (32.0 * (double)k.ng / (double)k.mg) + 8.0;
                 int kind;
-                if (lenA <= NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) kind = NCB_KS_KIND_SMALL;
+                // lenA < window: a row has at most lenA - 1 cells and the band moves by at most one
+                // column per row, so the thread kernel never reads past its window
+                if (lenA < NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) kind = NCB_KS_KIND_SMALL;
                 else if (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL) kind = NCB_KS_KIND_LARGE;
                 else kind = NCB_KS_KIND_HUGE;
                 bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
@@ -224,11 +226,12 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
         // the cell above and the reciprocal of the next column are fetched before this column's
         // store (they never alias it: src > jj), so shared-memory latency stays off the
         // loop-carried chain val -> val
-        double up = (shift < NCB_KS_SMALL_WINDOW) ? AT(shift) : 1.0;
+        // (src <= len + 1 < window: see the classification; slots right of the band hold 1.0)
+        double up = AT(shift);
         double r = rt[0];
         for (int jj = 0; jj < len; ++jj) {
             const int src = jj + 1 + shift;
-            const double up_next = (src < NCB_KS_SMALL_WINDOW) ? AT(src) : 1.0;
+            const double up_next = AT(src);
             const double r_next = rt[jj + 1];
             const double num = NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(val, dj));
             val = div_by_recip(num, di + dj, r);
