@@ -327,7 +327,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
             a.gmm_n3 = (int32_t *)h->gmm_n3.ptr;
         }
     }
-    ENSURE(h->wl_count, NCB_NUM_CLASSES * sizeof(int32_t));
+    ENSURE(h->wl_count, NCB_WL_COUNTERS * sizeof(int32_t));
     ENSURE(h->wl_list, (size_t)P * NCB_NUM_CLASSES * sizeof(int32_t));
     NcbWorklists wl;
     wl.class_count = (int32_t *)h->wl_count.ptr;

@@ -45,12 +45,14 @@ struct NcbDeviceArgs {
 //   class 0..2: one warp per position, 4 / 8 / 16 entries per lane
 //   class 3   : one 256-thread CTA per position, 8 entries per thread
 //   class 4   : one 1024-thread CTA per position, 10 entries per thread
-enum { NCB_NUM_CLASSES = 5 };
+enum { NCB_NUM_CLASSES = 5, NCB_NUM_PHASES = 4 };   // phases: statistics / mixture, 2 / 3 variables
+#define NCB_WL_COUNTERS (NCB_NUM_CLASSES * (1 + NCB_NUM_PHASES))
 static const int NCB_CLASS_CAP[NCB_NUM_CLASSES] = {128, 256, 512, 2048, NCB_MAX_READS};
 
 // worklists: class_count[c] positions in class_list[c * P ...]
 struct NcbWorklists {
-    int32_t *class_count;        // [NCB_NUM_CLASSES] device
+    int32_t *class_count;        // [NCB_NUM_CLASSES] device, followed by the work counters of the
+                                 // position kernels: [NCB_NUM_PHASES][NCB_NUM_CLASSES]
     int32_t *class_list;         // [NCB_NUM_CLASSES][P] device
 };
 
