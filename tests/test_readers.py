@@ -175,6 +175,38 @@ def test_bam_errors(tmp_path):
     assert R.NativeBam(path).read_uncalled4('other', 10, 'RNA002')[0].shape == (0, 10)
 
 
+def test_bam_edge_files(tmp_path):
+    """Header-only files, truncation in the middle of a block, the same read id in two samples."""
+    from nanocompore_b200 import _lib as L
+    rng = np.random.default_rng(12)
+    refs = [('tx', 120)]
+    empty = str(tmp_path / 'header_only.bam')
+    SF.write_bam(empty, refs, [])
+    bam = R.NativeBam(empty)
+    assert bam.references == ['tx'] and bam.count('tx') == 0 and bam.mapped_references() == {}
+    assert bam.read_uncalled4('tx', 120, 'RNA002')[0].shape == (0, 120)
+
+    reads = [SF.make_uncalled4_read(rng, 120, 'RNA002', f'r{k}') for k in range(30)]
+    full = str(tmp_path / 'full.bam')
+    SF.write_bam(full, refs, reads, block_bytes=900)
+    raw = open(full, 'rb').read()
+    cut = str(tmp_path / 'cut.bam')
+    open(cut, 'wb').write(raw[:len(raw) // 2])
+    with pytest.raises(L.NcbError):
+        R.NativeBam(cut)
+
+    # one read id present in two samples: both copies are kept, in the config order of the samples
+    paths = []
+    for s in ('kd1', 'kd2', 'wt1', 'wt2'):
+        p = str(tmp_path / f'{s}_dup.bam')
+        SF.write_bam(p, refs, [SF.make_uncalled4_read(rng, 120, 'RNA002', 'same-id', n_segments=1),
+                               SF.make_uncalled4_read(rng, 120, 'RNA002', f'only-{s}', n_segments=1)])
+        paths.append(p)
+    rows = R.Uncalled4Reader(bam_config(paths, max_invalid_kmers_freq=1.1)).read('tx', 120)
+    assert list(rows.read_names) == ['only-kd1', 'only-kd2', 'only-wt1', 'only-wt2'] + ['same-id'] * 4
+    assert list(rows.sample_ids) == [0, 1, 2, 3, 0, 1, 2, 3]
+
+
 def synthetic_dbs(tmp_path, seed, P=150):
     rng = np.random.default_rng(seed)
     paths = {}
