@@ -23,6 +23,10 @@ struct ncb_handle {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // events of the last timed batch
     bool timed = false;
     std::vector<cudaEvent_t> ev_log;   // 5 events per timed batch since ncb_set_timing(h, 1)
+    // the exact-KS kernels of a batch depend on its statistics kernels only: they run on this
+    // stream next to the mixture kernels (fork after the statistics phase, join before the results)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
@@ -147,6 +151,13 @@ int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
         delete h;
         return NCB_ERR_CUDA;
     }
+    if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        fprintf(stderr, "libncb: cannot create streams on device %d (%s)\n", device, cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return NCB_ERR_CUDA;
+    }
     // table of reciprocals for the exact-KS kernels, filled once
     if (ensure(h, h->kw_rtab, NCB_KS_RTAB_SIZE * sizeof(double)) != NCB_OK ||
         ncb_launch_ks_rtab((double *)h->kw_rtab.ptr, nullptr) < 0 || cudaDeviceSynchronize() != cudaSuccess) {
@@ -179,6 +190,9 @@ void ncb_destroy(ncb_handle *h) {
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : h->ev_log) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->aux) cudaStreamDestroy(h->aux);
     delete h;
 }
 
@@ -345,15 +359,32 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     if (n < 0) return fail(h, NCB_ERR_CUDA, "classify launch", cudaGetLastError());
     h->launches += n;
     if (time_it) CK(cudaEventRecord(h->ev[1], s));
-    n = ncb_launch_position_kernels(a, wl, h->sm_count, s, time_it ? h->ev[2] : nullptr);
+    // Untimed batches fork after the statistics kernels: exact KS on the auxiliary stream, mixture
+    // kernels on the caller's, joined before the results are copied out.  Timed batches keep
+    // everything on one stream so that the events bracket each group of kernels alone.
+    const bool fork = !time_it && any_ks && a.zbuf;
+    n = ncb_launch_position_kernels(a, wl, h->sm_count, s, time_it ? h->ev[2] : nullptr, fork ? 1 : 3);
     if (n < 0) return fail(h, NCB_ERR_CUDA, "position kernel launch", cudaGetLastError());
     h->launches += n;
     if (time_it) CK(cudaEventRecord(h->ev[3], s));
+    cudaStream_t ks_stream = s;
+    if (fork) {
+        CK(cudaEventRecord(h->ev_fork, s));
+        CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+        ks_stream = h->aux;
+    }
     if (any_ks) {
         // rows NCB_PV_KS_INTENSITY, NCB_PV_KS_DWELL are the first two rows of pvalues: [2][P]
-        n = ncb_launch_ks_pvalues(2 * P, a.ks_n0, a.ks_n1, a.ks_h, a.pvalues, kw, h->sm_count, s);
+        n = ncb_launch_ks_pvalues(2 * P, a.ks_n0, a.ks_n1, a.ks_h, a.pvalues, kw, h->sm_count, ks_stream);
         if (n < 0) return fail(h, NCB_ERR_CUDA, "KS p-value launch", cudaGetLastError());
         h->launches += n;
+    }
+    if (fork) {
+        CK(cudaEventRecord(h->ev_join, h->aux));
+        n = ncb_launch_position_kernels(a, wl, h->sm_count, s, nullptr, 2);
+        if (n < 0) return fail(h, NCB_ERR_CUDA, "mixture kernel launch", cudaGetLastError());
+        h->launches += n;
+        CK(cudaStreamWaitEvent(s, h->ev_join, 0));
     }
     if (time_it) CK(cudaEventRecord(h->ev[4], s));
     h->timed = time_it;

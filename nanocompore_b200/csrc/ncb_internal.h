@@ -84,9 +84,10 @@ struct NcbKsWork {
 
 // launchers (each returns the number of kernels launched, or <0 on launch error)
 int ncb_launch_classify(const NcbDeviceArgs &a, const NcbWorklists &w, cudaStream_t s);
-// statistics kernels, then (if a.zbuf) mixture kernels; `between` (optional) is recorded between them
+// phases & 1: statistics kernels; phases & 2: (if a.zbuf) mixture kernels; `between` (optional) is
+// recorded after the statistics kernels
 int ncb_launch_position_kernels(const NcbDeviceArgs &a, const NcbWorklists &w, int sm_count,
-                                cudaStream_t s, cudaEvent_t between);
+                                cudaStream_t s, cudaEvent_t between, int phases);
 int ncb_launch_ks_pvalues(int64_t n_problems, const int32_t *n0, const int32_t *n1,
                           const int64_t *h, double *p_out, const NcbKsWork &w, int sm_count,
                           cudaStream_t s);
