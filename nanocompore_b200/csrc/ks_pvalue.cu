@@ -42,7 +42,9 @@ __device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   //
 /* A LARGE problem gets a whole CTA instead of a warp when it alone would outlast the batch: its
  * band cells exceed 1/KS_CTA_SHARE of all wavefront cells of the batch (about the number of warps
  * the wavefront kernel keeps resident), and at least KS_CTA_MIN_CELLS. */
+#ifndef KS_CTA_SHARE
 #define KS_CTA_SHARE 3072.0
+#endif
 #define KS_CTA_MIN_CELLS 131072.0
 
 struct KsProblem {
