@@ -209,6 +209,9 @@ def run_gpu_arm(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # pinned batches are allocated below: place this rank next to its GPU first (NCB_NUMA=0 skips)
+    from nanocompore_b200.numa import bind_rank_to_gpu_node
+    numa = bind_rank_to_gpu_node(local_rank, apply=os.environ.get('NCB_NUMA', '1') != '0')
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # NCCL prints its version banner on stdout when the communicator comes up; stdout must
@@ -435,6 +438,7 @@ def run_gpu_arm(args):
         "gpu_launches": total_launches,
         "final_gather": gathered,
         "clocks": clocks,
+        "numa": numa,
         "setup_s": {"generate_and_pack": t_gen},
     }
     print(json.dumps(line), flush=True)

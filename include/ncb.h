@@ -219,6 +219,28 @@ int ncb_ks_exact_pvalues(ncb_handle *h, int64_t n, const int32_t *n0, const int3
 int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
                int memory, void *stream);
 
+/* Sequence-context combination of p-value columns (Hou's weighted Fisher combination of
+ * dependent p-values): replaces TranscriptComparator._combine_context_pvalues
+ * (comparisons.py:436-474) with cross_corr_matrix (627-651) and combine_pvalues_hou (659-705),
+ * for n_tx transcripts and n_cols p-value columns in one launch.
+ *   tx_offsets  HOST int64[n_tx + 1]   rows of transcript t: tx_offsets[t] .. tx_offsets[t + 1]
+ *   pos         HOST int64[n]          reference position of every row (distinct within a transcript)
+ *   pvalues     float64[n_cols][n]     NaN = position not tested by that column   (`memory`)
+ *   weights     HOST float64[2 * context + 1]   (harmonic or uniform, comparisons.py:439-443)
+ *   combined    float64[n_cols][n]     NaN where the row's own p-value is NaN     (`memory`)
+ *   status      HOST int32[n_cols][n_tx]   NCB_CTX_*: where the reference raises, the status says
+ *                                       why and the rows of that (column, transcript) are NaN
+ * 1 <= context <= NCB_CTX_MAX.  The call returns when the results are in place. */
+#define NCB_CTX_MAX 8
+enum {
+    NCB_CTX_OK = 0,
+    NCB_CTX_TOO_SHORT = 1,       /* "Not enough p-values for a context of order" (comparisons.py:632-633) */
+    NCB_CTX_INVALID_PVALUE = 2   /* "At least one p-value is invalid" (comparisons.py:636-637)          */
+};
+int ncb_context_combine(ncb_handle *h, int64_t n_tx, const int64_t *tx_offsets, const int64_t *pos,
+                        int32_t n_cols, const double *pvalues, int32_t context, const double *weights,
+                        double *combined, int32_t *status, int memory, void *stream);
+
 /* --- host-side CSR packer (no GPU work) ---------------------------------------------
  * Dense per-transcript tensor of the reference's readers (run.py:621-855: data[P][R][V] float32,
  * NaN = the read does not cover the position) -> the NCB_LAYOUT_CSR arrays.  Two passes so that

@@ -25,6 +25,8 @@ NCB_POS_LOW_COVERAGE, NCB_POS_BAD_STD, NCB_POS_TOO_MANY_READS = 1, 2, 4
 NCB_POS_DROP_MASK = 7
 NCB_POS_AUTO_GMM = 256
 NCB_POS_MW_EXACT_SKIPPED = 512
+NCB_CTX_MAX = 8
+NCB_CTX_OK, NCB_CTX_TOO_SHORT, NCB_CTX_INVALID_PVALUE = 0, 1, 2
 
 PV = dict(KS_INTENSITY=0, KS_DWELL=1, MW_INTENSITY=2, MW_DWELL=3, TT_INTENSITY=4, TT_DWELL=5,
           GMM_CHI2=6, GMM_LOGIT=7, GMM_LOGIT_COEF=8)
@@ -46,6 +48,7 @@ NCB_DF_ROWS = 17
 
 EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
+           'ncb_context_combine',
            'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals',
            'ncb_pack_count', 'ncb_pack_fill', 'ncb_pack_rows_count', 'ncb_pack_rows_fill',
            'ncb_rows_invalid_ratio', 'ncb_bam_open', 'ncb_bam_close', 'ncb_bam_last_error',
@@ -114,6 +117,8 @@ def load(path=None):
     lib.ncb_ks_exact_pvalues.restype = C.c_int
     lib.ncb_bh_fdr.argtypes = [vp, i64, vp, vp, C.c_double, C.c_int, vp]
     lib.ncb_bh_fdr.restype = C.c_int
+    lib.ncb_context_combine.argtypes = [vp, i64, vp, vp, i32, vp, i32, vp, vp, vp, C.c_int, vp]
+    lib.ncb_context_combine.restype = C.c_int
     lib.ncb_kernel_launches.argtypes = [vp]
     lib.ncb_kernel_launches.restype = i64
     lib.ncb_set_timing.argtypes = [vp, C.c_int]

@@ -20,7 +20,7 @@ INCLUDE = os.path.join(ROOT, 'include')
 OBJDIR = os.path.join(ROOT, 'build', 'ncb')
 LIB = os.path.join(HERE, 'libncb.so')
 
-SOURCES = ['position_kernel.cu', 'ks_pvalue.cu', 'fdr.cu', 'api.cu', 'pack.cu', 'reader.cu']
+SOURCES = ['position_kernel.cu', 'ks_pvalue.cu', 'fdr.cu', 'context.cu', 'api.cu', 'pack.cu', 'reader.cu']
 HEADERS = [os.path.join(CSRC, h) for h in ('ncb_internal.h', 'ncb_math.cuh', 'group_ops.cuh')] + \
           [os.path.join(INCLUDE, 'ncb.h')]
 

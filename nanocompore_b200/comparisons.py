@@ -70,6 +70,7 @@ class TranscriptComparator:
         self._worker = worker
         self._with_logit = with_logit
         self._engines = {}
+        self._context_engine = None     # the engine of the last comparison: it also combines contexts
 
     # ------------------------------------------------------------------ engine
     def _engine(self, device):
@@ -94,6 +95,7 @@ class TranscriptComparator:
                 min_coverage=0,            # Worker._filter_low_cov_positions already ran
                 dwell_is_raw=False,        # Worker._prepare_data already took the log10
                 cluster_counts=self._config.get_cluster_counts())
+        self._context_engine = self._engines[index]
         return self._engines[index]
 
     def _depleted_condition_id(self):
@@ -211,8 +213,10 @@ class TranscriptComparator:
             for test in self._get_test_masks(None, n_positions):
                 columns.update(self._test_columns(test, pv, st, counts, status, transcript))
             if context > 0:
-                for test in [col for col in columns if 'pvalue' in col]:
-                    columns[f"{test}_context_{context}"] = self._combine_context(pos, columns[test])
+                tests = [col for col in columns if 'pvalue' in col]
+                combined = self._combine_context(pos, [columns[test] for test in tests])
+                for test, values in zip(tests, combined):
+                    columns[f"{test}_context_{context}"] = values
             # the index keeps the row labels of the unfiltered frame, like the reference's drop()
             return pd.DataFrame(columns, index=np.arange(keep.size)[keep])
 
@@ -228,8 +232,10 @@ class TranscriptComparator:
             self._merge_results(results, test_results, test, mask, auto_test_mask, n_positions)
         if context > 0:
             tests = [col for col in results.columns if 'pvalue' in col]
-            for test in tests:
-                results[f"{test}_context_{context}"] = self._combine_context_pvalues(results, test)
+            combined = self._combine_context(results.pos.to_numpy(),
+                                             [results[test].to_numpy(dtype=float) for test in tests])
+            for test, values in zip(tests, combined):
+                results[f"{test}_context_{context}"] = values
         return results
 
     def _get_test_masks(self, auto_test_mask, n_positions):
@@ -288,23 +294,31 @@ class TranscriptComparator:
                 results.loc[rows, 'auto_pvalue'] = results.loc[rows, column]
 
     def _combine_context_pvalues(self, results, test):
-        return self._combine_context(results.pos.to_numpy(), results[test].to_numpy(dtype=float))
+        return self._combine_context(results.pos.to_numpy(), [results[test].to_numpy(dtype=float)])[0]
 
-    def _combine_context(self, pos, pvalues):
-        # comparisons.py:436-474 (host side).  Same arithmetic as the reference's
-        # per-window combine_pvalues_hou, evaluated for all windows of the transcript at once.
+    def _combine_context(self, pos, columns):
+        """comparisons.py:436-474 for every p-value column of the transcript in one
+        ``ncb_context_combine`` call: dense track, correlation of the track with
+        its shifts, Hou's combination per row -- all in the context kernel.  Where the reference
+        raises (cross_corr_matrix, comparisons.py:632-637) this raises the same error."""
         context = self._config.get_sequence_context()
         if self._config.get_sequence_context_weights() == "harmonic":
             weights = harmomic_series(context)
         else:
             weights = [1] * (2 * context + 1)
+        if self._context_engine is None:
+            raise NanocomporeError("no libncb engine: the context combination runs on the GPU "
+                                   "(nanocompore_b200 has no CPU path)")
+        if context > L.NCB_CTX_MAX:
+            raise NanocomporeError(f"sequence_context {context} is larger than NCB_CTX_MAX = {L.NCB_CTX_MAX}")
         pos = np.asarray(pos).astype(np.int64)
-        idx = pos - pos.min()
-        padded = np.ones(int(idx.max()) + 1 + 2 * context, dtype=float)
-        padded[idx + context] = np.asarray(pvalues, dtype=float)
-        corr = cross_corr_matrix(padded[context:-context], context)
-        windows = np.lib.stride_tricks.sliding_window_view(padded, 2 * context + 1)
-        return combine_windows_hou(windows, weights, corr, context)[idx]
+        pvalues = np.stack([np.asarray(c, dtype=np.float64) for c in columns])
+        combined, status = self._context_engine.context_combine([0, pos.size], pos, pvalues, context, weights)
+        if (status == L.NCB_CTX_TOO_SHORT).any():
+            raise RuntimeError("Not enough p-values for a context of order %s" % context)
+        if (status == L.NCB_CTX_INVALID_PVALUE).any():
+            raise RuntimeError("At least one p-value is invalid")
+        return list(combined)
 
     def retry(self, fn, delay=5, backoff=5, max_attempts=3, exception=Exception):
         # comparisons.py:608-619; libncb sizes its scratch per batch, so OOM is not expected
@@ -387,41 +401,6 @@ def cross_corr_matrix(pvalues, context=2):
         for y in range(x + 1):
             matrix[x, y] = matrix[y, x] = np.corrcoef(shifted[x], shifted[y])[0, 1]
     return matrix
-
-
-def combine_windows_hou(windows, weights, cor_mat, centre):
-    """``combine_pvalues_hou`` for every row of ``windows`` (n, k) at once: NaN where the centre of
-    the window is NaN, NaNs elsewhere in a window count as 1 (comparisons.py:463-472)."""
-    from scipy.stats import chi2
-    windows = np.asarray(windows, dtype=np.float64)
-    w = np.asarray(weights, dtype=np.float64)
-    k = w.size
-    centre_nan = np.isnan(windows[:, centre])
-    p = np.nan_to_num(windows, nan=1.0)
-    live = ~centre_nan
-    if ((p[live] == 0) | np.isinf(p[live]) | (p[live] > 1)).any():
-        raise ValueError("At least one p-value is invalid")
-    # the scalar sums of combine_pvalues_hou, accumulated in the same order
-    cov_sum = np.float64(0)
-    for i in range(k):
-        for j in range(i + 1, k):
-            r = cor_mat[i][j]
-            cov_sum += w[i] * w[j] * ((3.263 * r) + (0.710 * r ** 2) + (0.027 * r ** 3))
-    sw_sum = np.float64(0)
-    w_sum = np.float64(0)
-    for i in range(k):
-        sw_sum += w[i] ** 2
-        w_sum += w[i]
-    tau = np.zeros(p.shape[0])
-    with np.errstate(divide='ignore'):
-        for i in range(k):
-            tau = tau + w[i] * (-2 * np.log(p[:, i]))
-    scale = (2 * sw_sum + cov_sum) / (2 * w_sum)
-    dof = (4 * w_sum ** 2) / (2 * sw_sum + cov_sum)
-    out = chi2.sf(tau / scale, dof)
-    out = np.where(out == 0, np.finfo(np.float64).tiny, out)
-    out = np.where((p == 1).all(1), 1.0, out)
-    return np.where(centre_nan, np.nan, out)
 
 
 def combine_pvalues_hou(pvalues, weights, cor_mat):

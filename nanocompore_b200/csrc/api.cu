@@ -35,6 +35,7 @@ struct ncb_handle {
     DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch, kw_rtab;
     DevBuf fdr_scratch, fdr_p, fdr_q;
     DevBuf unit_a, unit_b, unit_c, unit_d;
+    DevBuf ctx_tx, ctx_track, ctx_idx, ctx_p, ctx_tracks, ctx_out, ctx_status;
 };
 
 static int fail(ncb_handle *h, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -187,7 +188,8 @@ void ncb_destroy(ncb_handle *h) {
                      &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
                      &h->ks_h, &h->zbuf, &h->gmm_n, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
                      &h->kw_bin, &h->kw_fetch, &h->kw_rtab, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
-                     &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d};
+                     &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d,
+                     &h->ctx_tx, &h->ctx_track, &h->ctx_idx, &h->ctx_p, &h->ctx_tracks, &h->ctx_out, &h->ctx_status};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : h->ev_log) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -475,6 +477,70 @@ int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues,
         CK(cudaMemcpyAsync(qvalues, dq, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }
+    return NCB_OK;
+}
+
+int ncb_context_combine(ncb_handle *h, int64_t n_tx, const int64_t *tx_offsets, const int64_t *pos,
+                        int32_t n_cols, const double *pvalues, int32_t context, const double *weights,
+                        double *combined, int32_t *status, int memory, void *stream) {
+    if (!h) return NCB_ERR_INVALID;
+    if (context < 1 || context > NCB_CTX_MAX) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: context out of range");
+    if (n_tx < 0 || n_cols < 0 || n_tx > 0x7fffffffLL || n_cols > 65535)
+        return fail(h, NCB_ERR_INVALID, "ncb_context_combine: size out of range");
+    if (n_tx == 0 || n_cols == 0) return NCB_OK;
+    if (!tx_offsets || !weights || !status) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: null pointer");
+    const int64_t n = tx_offsets[n_tx];
+    if (tx_offsets[0] != 0 || n < 0) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: bad tx_offsets");
+    if (n > 0 && (!pos || !pvalues || !combined)) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: null pointer");
+    // the dense track of a transcript spans its first to its last position (comparisons.py:445-459)
+    std::vector<int64_t> track(n_tx + 1, 0);
+    std::vector<int32_t> idx((size_t)n);
+    for (int64_t t = 0; t < n_tx; ++t) {
+        const int64_t r0 = tx_offsets[t], r1 = tx_offsets[t + 1];
+        if (r1 < r0 || r1 > n) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: bad tx_offsets");
+        int64_t len = 0;
+        if (r1 > r0) {
+            int64_t lo = pos[r0], hi = pos[r0];
+            for (int64_t r = r0 + 1; r < r1; ++r) {
+                lo = pos[r] < lo ? pos[r] : lo;
+                hi = pos[r] > hi ? pos[r] : hi;
+            }
+            len = hi - lo + 1;
+            if (len > 0x7fffffffLL / 2) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: positions span too wide");
+            for (int64_t r = r0; r < r1; ++r) idx[(size_t)r] = (int32_t)(pos[r] - lo);
+        }
+        track[t + 1] = track[t] + len;
+    }
+    const int64_t total = track[n_tx];
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    ENSURE(h->ctx_tx, (size_t)(n_tx + 1) * 8);
+    ENSURE(h->ctx_track, (size_t)(n_tx + 1) * 8);
+    ENSURE(h->ctx_idx, (size_t)n * 4);
+    ENSURE(h->ctx_tracks, (size_t)total * n_cols * 8);
+    ENSURE(h->ctx_status, (size_t)n_tx * n_cols * 4);
+    CK(cudaMemcpyAsync(h->ctx_tx.ptr, tx_offsets, (size_t)(n_tx + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->ctx_track.ptr, track.data(), (size_t)(n_tx + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (n) CK(cudaMemcpyAsync(h->ctx_idx.ptr, idx.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    const double *dp = pvalues;
+    double *dout = combined;
+    if (memory == NCB_MEM_HOST) {
+        ENSURE(h->ctx_p, (size_t)n * n_cols * 8);
+        ENSURE(h->ctx_out, (size_t)n * n_cols * 8);
+        if (n) CK(cudaMemcpyAsync(h->ctx_p.ptr, pvalues, (size_t)n * n_cols * 8, cudaMemcpyHostToDevice, s));
+        dp = (const double *)h->ctx_p.ptr;
+        dout = (double *)h->ctx_out.ptr;
+    }
+    int k = ncb_launch_context(n_tx, n, total, n_cols, (const int64_t *)h->ctx_tx.ptr,
+                               (const int64_t *)h->ctx_track.ptr, (const int32_t *)h->ctx_idx.ptr, dp,
+                               (double *)h->ctx_tracks.ptr, dout, (int32_t *)h->ctx_status.ptr, context,
+                               weights, s);
+    if (k < 0) return fail(h, NCB_ERR_CUDA, "context combination launch", cudaGetLastError());
+    h->launches += k;
+    if (memory == NCB_MEM_HOST && n)
+        CK(cudaMemcpyAsync(combined, dout, (size_t)n * n_cols * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, h->ctx_status.ptr, (size_t)n_tx * n_cols * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));   // also keeps the staging vectors alive until the copies are done
     return NCB_OK;
 }
 

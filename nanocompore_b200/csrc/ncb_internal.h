@@ -96,4 +96,8 @@ int ncb_launch_ks_rtab(double *rtab, cudaStream_t s);
 int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, void *scratch,
                       size_t scratch_bytes, cudaStream_t s);
 size_t ncb_bh_fdr_scratch_bytes(int64_t n);
+int ncb_launch_context(int64_t n_tx, int64_t n_rows, int64_t track_total, int32_t n_cols,
+                       const int64_t *tx_offsets, const int64_t *track_offsets, const int32_t *idx,
+                       const double *pvalues, double *tracks, double *combined, int32_t *status,
+                       int32_t context, const double *weights, cudaStream_t s);
 int ncb_configure_kernels(void);  // cudaFuncSetAttribute for large dynamic shared memory

@@ -99,6 +99,46 @@ NCB_HD inline double student_t_two_sided(double t, double df) {
     return clip01(incbet(0.5 * df, 0.5, df / den, t2 / den));
 }
 
+// Regularised upper incomplete gamma function Q(a, x) = chi2.sf(2x, 2a) for a > 0: the power
+// series of P for x < a + 1, the continued fraction of Q (modified Lentz) otherwise.  Used by
+// the sequence-context combination (comparisons.py:700: chi2.sf(tau / c, f) with a fractional
+// number of degrees of freedom).
+NCB_HD inline double igamc(double a, double x) {
+    if (a != a || x != x || !(a > 0.0)) return ncb_nan();
+    if (!(x > 0.0)) return x == 0.0 ? 1.0 : ncb_nan();
+    if (isinf(x)) return 0.0;
+    const double lfront = a * log(x) - x - lgamma(a);   // log of x^a e^-x / Gamma(a)
+    if (x < a + 1.0) {
+        double term = 1.0 / a, sum = term, ap = a;
+        for (int n = 0; n < 10000; ++n) {
+            ap += 1.0;
+            term *= x / ap;
+            sum += term;
+            if (term < sum * 1e-17) break;
+        }
+        return clip01(1.0 - sum * exp(lfront));
+    }
+    // SciPy's routine (cephes igam_fac) gives up once the factor x^a e^-x / Gamma(a) is below
+    // exp(-MAXLOG) and returns 0 instead of a denormal; the caller replaces 0 by the smallest
+    // normal number (comparisons.py:702-704), so the same cut is needed here
+    if (lfront < -7.09782712893383996843e2) return 0.0;
+    const double TINY = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / TINY, d = 1.0 / b, h = d;
+    for (int i = 1; i < 10000; ++i) {
+        const double an = -(double)i * ((double)i - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < TINY) d = TINY;
+        c = b + an / c;
+        if (fabs(c) < TINY) c = TINY;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return clip01(exp(lfront) * h);
+}
+
 NCB_HD inline long long gcd_ll(long long a, long long b) {
     while (b) { long long t = a % b; a = b; b = t; }
     return a;

@@ -352,6 +352,39 @@ class Engine:
                                         float(scale), L.NCB_MEM_HOST, self._stream()))
         return q
 
+    def context_combine(self, tx_offsets, pos, pvalues, context, weights):
+        """Hou's sequence-context combination (comparisons.py:436-474, 627-705) of ``pvalues``
+        [n_cols, n] over the transcripts delimited by ``tx_offsets`` (rows of transcript t:
+        tx_offsets[t]..tx_offsets[t+1]; ``pos`` = reference position of every row).  Returns
+        (combined [n_cols, n], status [n_cols, n_tx]) -- ``status`` holds NCB_CTX_* where the
+        reference raises.  ``pvalues`` may be a numpy array (host) or a CUDA float64 tensor."""
+        tx_offsets = np.ascontiguousarray(tx_offsets, dtype=np.int64)
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        context = int(context)
+        if weights.size != 2 * context + 1:
+            raise ValueError("context_combine: 2 * context + 1 weights are needed")
+        n_tx = tx_offsets.size - 1
+        on_device = isinstance(pvalues, torch.Tensor) and pvalues.is_cuda
+        if on_device:
+            p = pvalues.to(torch.float64).contiguous()
+            p = p.reshape(1, -1) if p.dim() == 1 else p
+            out = torch.empty_like(p)
+            p_ptr, out_ptr, n_cols, n = p.data_ptr(), out.data_ptr(), p.shape[0], p.shape[1]
+        else:
+            p = np.ascontiguousarray(pvalues, dtype=np.float64)
+            p = p.reshape(1, -1) if p.ndim == 1 else p
+            out = np.empty_like(p)
+            p_ptr, out_ptr, n_cols, n = p.ctypes.data, out.ctypes.data, p.shape[0], p.shape[1]
+        if n != pos.size or (n_tx >= 0 and tx_offsets[-1] != n):
+            raise ValueError("context_combine: tx_offsets / pos / pvalues disagree on the number of rows")
+        status = np.zeros((n_cols, max(n_tx, 0)), dtype=np.int32)
+        self._check(self.lib.ncb_context_combine(
+            self._handle, n_tx, tx_offsets.ctypes.data, pos.ctypes.data, n_cols, p_ptr, context,
+            weights.ctypes.data, out_ptr, status.ctypes.data,
+            L.NCB_MEM_DEVICE if on_device else L.NCB_MEM_HOST, self._stream()))
+        return out, status
+
     # ------------------------------------------------------------------ introspection
     def kernel_launches(self):
         return int(self.lib.ncb_kernel_launches(self._handle))

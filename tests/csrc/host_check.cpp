@@ -18,5 +18,6 @@ double hc_ks_equal_p(long long n, long long h) { return ncb::ks_equal_p(n, h); }
 void hc_quot_rn(const double *a, const double *b, double *q, long long n) {
     for (long long i = 0; i < n; ++i) q[i] = ncb::quot_rn(a[i], b[i], 1.0 / b[i]);
 }
+double hc_igamc(double a, double x) { return ncb::igamc(a, x); }
 double hc_normal_two_sided(double z) { return ncb::normal_two_sided(z); }
 }

@@ -75,17 +75,17 @@ def test_auto_routing_columns():
     assert df['KS_intensity_pvalue'][is_gmm].isna().all() and df['GMM_chi2_pvalue'][~is_gmm].isna().all()
 
 
-def test_context_columns_follow_every_pvalue_column():
+def test_context_columns_need_the_gpu():
+    """The context combination is a libncb kernel (ncb_context_combine): without an engine the
+    frame cannot be assembled -- there is no host path to fall back to."""
+    from nanocompore_b200.comparisons import NanocomporeError
     rng = np.random.default_rng(3)
     P = 60
     status, pv, st, counts = columns(P, rng)
     cfg = PathConfig(dict(data=DATA, depleted_condition='kd', comparison_methods=['KS'], sequence_context=2))
-    df = TranscriptComparator(cfg, Worker())._assemble(Transcript, torch.arange(P, dtype=torch.int16),
-                                                       status, pv, st, counts, False)
-    assert list(df.columns[-2:]) == ['KS_intensity_pvalue_context_2', 'KS_dwell_pvalue_context_2']
-    from oracle.context import combine_context_pvalues
-    want = combine_context_pvalues(np.arange(P), pv[L.PV['KS_INTENSITY']], 2)
-    np.testing.assert_allclose(df['KS_intensity_pvalue_context_2'].to_numpy(), want, rtol=1e-12)
+    with pytest.raises(NanocomporeError, match="no CPU path"):
+        TranscriptComparator(cfg, Worker())._assemble(Transcript, torch.arange(P, dtype=torch.int16),
+                                                      status, pv, st, counts, False)
 
 
 def test_too_many_reads_raises():

@@ -168,8 +168,13 @@ def test_sequence_context_columns_match_the_oracle():
     z = load('synthetic_ref.npz')
     df = compare(config(comparison_methods=['KS'], sequence_context=2, sequence_context_weights='harmonic'),
                  z['case0/prepared'], z['case0/samples'], z['case0/conditions'], z['case0/prepared_positions'])
-    want = combine_context_pvalues(df['pos'].to_numpy(), df['KS_intensity_pvalue'].to_numpy(), 2, 'harmonic')
-    np.testing.assert_allclose(df['KS_intensity_pvalue_context_2'].to_numpy(), want, rtol=1e-12, equal_nan=True)
+    assert list(df.columns[-2:]) == ['KS_intensity_pvalue_context_2', 'KS_dwell_pvalue_context_2']
+    for var in ('intensity', 'dwell'):
+        want = combine_context_pvalues(df['pos'].to_numpy(), df[f'KS_{var}_pvalue'].to_numpy(), 2, 'harmonic')
+        got = df[f'KS_{var}_pvalue_context_2'].to_numpy()
+        assert (np.isnan(got) == np.isnan(want)).all()
+        m = ~np.isnan(want)
+        np.testing.assert_allclose(np.log10(got[m]), np.log10(want[m]), rtol=1e-5, atol=1e-8)
 
 
 def test_unsupported_options_raise():

@@ -34,6 +34,7 @@ def hc():
     lib.hc_ks_prob_outside_square.restype = d; lib.hc_ks_prob_outside_square.argtypes = [ll, ll]
     lib.hc_ks_equal_p.restype = d; lib.hc_ks_equal_p.argtypes = [ll, ll]
     lib.hc_normal_two_sided.restype = d; lib.hc_normal_two_sided.argtypes = [d]
+    lib.hc_igamc.restype = d; lib.hc_igamc.argtypes = [d, d]
     lib.hc_quot_rn.restype = None; lib.hc_quot_rn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, ll]
     return lib
 
@@ -167,3 +168,26 @@ def test_quotient_from_reciprocal_is_the_division(hc):
     q = np.empty(n)
     hc.hc_quot_rn(a.ctypes.data, b.ctypes.data, q.ctypes.data, n)
     assert np.array_equal(q, a / b)
+
+
+def test_igamc_against_scipy(hc):
+    # chi2.sf(t, f) = Q(f/2, t/2) with the fractional degrees of freedom Hou's combination
+    # produces (comparisons.py:696-700): f in (0, 2k], k = 2*context + 1 terms
+    from scipy.special import gammaincc
+    rng = np.random.default_rng(5)
+    a = np.concatenate([rng.uniform(0.05, 12.0, 4000), [0.5, 1.0, 2.5, 5.0, 8.5]])
+    x = np.concatenate([10.0 ** rng.uniform(-6, 2.95, 4000), [0.0, 1.0, 700.0, 745.0, 2000.0]])
+    worst = 0.0
+    for ai, xi in zip(a, x):
+        got, want = hc.hc_igamc(ai, xi), float(gammaincc(ai, xi))
+        assert close_log10(got, want, rtol=1e-9, atol=1e-12), (ai, xi, got, want)
+        if want > 1e-300:
+            worst = max(worst, abs(got - want) / want)
+    assert worst < 1e-9
+    # the denormal range is flushed to 0 exactly where SciPy does
+    for ai, xi in [(5.056802588890762, 765.6748459794617), (4.8176392460683, 742.9093387455972),
+                   (4.8176392460683, 735.0), (2.5, 712.0), (2.5, 716.0), (2.5, 720.0)]:
+        assert (hc.hc_igamc(ai, xi) == 0.0) == (float(gammaincc(ai, xi)) == 0.0), (ai, xi)
+    assert hc.hc_igamc(3.0, 0.0) == 1.0
+    assert hc.hc_igamc(3.0, float('inf')) == 0.0
+    assert np.isnan(hc.hc_igamc(3.0, float('nan')))
