@@ -46,6 +46,7 @@ __device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   //
 #define KS_CTA_SHARE 3072.0
 #endif
 #define KS_CTA_MIN_CELLS 131072.0
+#define KS_SMALL_MAX_CELLS 16384.0   /* band cells a single thread may walk (~0.4 ms) */
 
 struct KsProblem {
     int m, n;            // m >= n
@@ -107,7 +108,9 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
                 int kind;
                 // lenA < window: a row has at most lenA - 1 cells and the band moves by at most one
                 // column per row, so the thread kernel never reads past its window
-                if (lenA < NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE) kind = NCB_KS_KIND_SMALL;
+                // (and a thread walks its problem alone: the long ones go to a warp)
+                if (lenA < NCB_KS_SMALL_WINDOW && a + b < KS_RECIP_TABLE && (double)k.m * width <= KS_SMALL_MAX_CELLS)
+                    kind = NCB_KS_KIND_SMALL;
                 else if (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL) kind = NCB_KS_KIND_LARGE;
                 else kind = NCB_KS_KIND_HUGE;
                 bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
@@ -259,13 +262,96 @@ __global__ void ks_rtab_kernel(double *rtab) {
 }
 
 // ---- thread per problem: equal sizes -----------------------------------------------------
+// The Horner product of ks_prob_outside_square (ncb_math.cuh) with the bits of its n divisions
+// but not their cost: numerators and denominators run as doubles (exact integers), the quotient
+// by the integer n + k h + j + 1 comes from the handle's table of correctly rounded reciprocals
+// (div_by_recip: the correctly rounded quotient).  The quotient trick needs normal numbers, so a
+// factor that has fallen below 1e-270 finishes its block with true divisions; a factor that has
+// reached zero stays zero.  At 5000 reads per condition this is 40 instead of ~1300 cycles per
+// term (64-bit integer conversions and a division in the chain).
+__device__ double ks_prob_outside_square_fast(int n, int h, const double *__restrict__ rtab) {
+    double P = 0.0;
+    for (int k = n / h; k >= 0; --k) {
+        double p1 = 1.0;
+        double a = (double)(n - k * h);            // numerator n - k h - j
+        int b = n + k * h + 1;                     // denominator n + k h + j + 1
+        double bd = (double)b;
+        int j = 0;
+        for (; j < h && p1 >= 1e-270; ++j) {
+            p1 = div_by_recip(NCB_DMUL(a, p1), bd, __ldg(rtab + b));
+            a -= 1.0; bd += 1.0; ++b;
+        }
+        for (; j < h && p1 != 0.0; ++j) {
+            p1 = NCB_DDIV(NCB_DMUL(a, p1), bd);
+            a -= 1.0; bd += 1.0;
+        }
+        if (j < h) p1 = 0.0;                       // (+-0 either way: only 1 - P is taken from it)
+        P = NCB_DMUL(p1, NCB_DADD(1.0, -P));
+    }
+    return 2.0 * P;
+}
+
 __global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_out, NcbKsWork w) {
     const int lo = w.hist[NCB_KS_KIND_EQUAL * NCB_KS_BUCKETS];
     const int hi = w.hist[(NCB_KS_KIND_EQUAL + 1) * NCB_KS_BUCKETS];
     const int idx = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= hi) return;
     const int q = w.list[idx];
-    p_out[q] = ks_equal_p(n0[q], h[q]);
+    const long long n = n0[q], hh = h[q];
+    // (the unit entry point accepts samples beyond the table: those take the plain form)
+    if (2 * n + 1 < NCB_KS_RTAB_SIZE && hh <= n)
+        p_out[q] = ks_equal_finish(ks_prob_outside_square_fast((int)n, (int)hh, w.rtab), n, hh);
+    else
+        p_out[q] = ks_equal_p(n, hh);
+}
+
+// ---- wavefront kernels ------------------------------------------------------------------------
+// One step of a wavefront computes one cell per row: row i = i0 + r is at column j = jlo - r + t
+// at step t, so i + j = i0 + jlo + t is the same for every row (one reciprocal per step, read from
+// the handle's table a step ahead) and the cell above is what row r - 1 computed in the step
+// before.  Everything a step needs besides the two neighbours is carried incrementally: the
+// column as an int (ring index) and as a double, the divisor, the band coordinate
+// v = ng i - mg j (inside the band iff |v| < h).  The step is branch free: every lane computes,
+// the selects decide what is kept (outside the band a cell is 1, outside the chunk's column range
+// nothing changes).
+struct WaveRow {
+    double di, dj, den, left, cur;
+    int j, jr, v;            // column, column - jlo, ng i - mg j
+    unsigned span;           // jhi - jlo for a live row, 0 for a row past the last one
+};
+
+__device__ __forceinline__ void wave_row_init(WaveRow &r, int i, int r_idx, bool on, int i0, int jlo, int jhi,
+                                              int ng, int mg) {
+    r.di = (double)i;
+    r.j = jlo - r_idx;
+    r.jr = -r_idx;
+    r.dj = (double)r.j;
+    r.den = (double)(i0 + jlo);
+    r.v = ng * i - mg * r.j;
+    r.span = on ? (unsigned)(jhi - jlo) : 0u;
+    r.left = 1.0;
+    r.cur = 1.0;
+}
+
+// the cell of this step from `up` (cell above) and r.left; returns true if the row is inside the
+// chunk's column range (then r.cur / r.left hold the new cell)
+__device__ __forceinline__ bool wave_cell(WaveRow &r, double up, double rden, int hh) {
+    const bool active = (unsigned)r.jr < r.span;
+    const bool inside = (unsigned)(r.v + hh - 1) < (unsigned)(2 * hh - 1);
+    const double val = div_by_recip(NCB_DADD(NCB_DMUL(up, r.di), NCB_DMUL(r.left, r.dj)), r.den, rden);
+    const double x = inside ? val : 1.0;
+    r.cur = active ? x : r.cur;
+    r.left = r.cur;
+    return active;
+}
+__device__ __forceinline__ void wave_advance(WaveRow &r, int mg) {
+    ++r.j; ++r.jr; r.v -= mg;
+    r.dj += 1.0; r.den += 1.0;
+}
+
+// reciprocal of k: from the table, or (unit entry point, samples beyond the table) computed
+__device__ __forceinline__ double wave_recip(const double *__restrict__ rtab, int k) {
+    return k < NCB_KS_RTAB_SIZE ? __ldg(rtab + k) : __drcp_rn((double)k);
 }
 
 // ---- warp per problem: skewed wavefront over 32 rows --------------------------------------
@@ -273,161 +359,173 @@ __global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_o
 // by j & (RING - 1).  The band moves to the right, so a slot is reused only by columns RING
 // apart; classification guarantees RING >= the widest span a chunk touches (or RING > n, in
 // which case the ring never wraps).  Slots that enter the band for the first time must read 1
-// ("outside the band"): they are reset at the end of the chunk before.
-template <int WARPS, int RING, bool WRAP>
-__global__ void __launch_bounds__(WARPS * 32)
-ks_warp_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out,
-               NcbKsWork w, int kind) {
-    extern __shared__ double rows_all[];   // [WARPS][RING]
-    const int lane = threadIdx.x & 31;
-    double *prev = rows_all + (size_t)(threadIdx.x >> 5) * RING;
-    constexpr int MASK = WRAP ? RING - 1 : -1;   // WRAP = false: RING > n, plain indexing
-    static_assert(!WRAP || (RING & (RING - 1)) == 0, "ring size must be a power of two");
-    const int lo = w.hist[kind * NCB_KS_BUCKETS] + w.fetch[NCB_KS_KINDS];   // the dearest go to the CTA kernel
-    const int hi = w.hist[(kind + 1) * NCB_KS_BUCKETS];
-    for (;;) {
-        int idx = 0;
-        if (lane == 0) idx = lo + atomicAdd(&w.fetch[kind], 1);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= hi) break;
-        const int q = w.list[idx];
-        const KsProblem k = make_problem(n0[q], n1[q], h[q]);
-        // every quantity below fits in 32 bits: n0 + n1 <= NCB_MAX_READS, so ng*i, mg*j and
-        // h <= lcm are at most 5120 * 5120
-        const int n = k.n, m = k.m;
-        const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
-        const int maxj0 = min((hh + mg - 1) / mg, n + 1);
-        const int fill = min(n + 1, RING);
-        for (int j = lane; j < fill; j += 32) prev[j] = (j < maxj0) ? 0.0 : 1.0;
-        __syncwarp();
-        int jhi_done = min(n + 1, RING);          // columns below this hold valid ring slots
-        for (int i0 = 1; i0 <= m; i0 += 32) {
-            const int rows = min(32, m - i0 + 1);
-            const int ilast = i0 + rows - 1;
-            const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
-            const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);
-            const int jhi = min((ng * ilast + hh + mg - 1) / mg, n + 1);
-            // slots entering the band in this chunk that were last used RING columns ago
-            for (int j = jhi_done + lane; j < jhi; j += 32) prev[j & MASK] = 1.0;
-            jhi_done = max(jhi_done, jhi);
-            __syncwarp();
-            const int i = i0 + lane;
-            const bool row_on = lane < rows;
-            const double di = (double)i;
-            const int ngi = ng * i;
-            double left = 1.0, cur = 1.0;
-            const int nsteps = (jhi - jlo) + rows - 1;
-            int j = jlo - lane;
-            double dj = (double)j;
-            double den = (double)(i0 + jlo);
-            // i + j = i0 + jlo + t on every lane: one reciprocal per step for the warp, read from
-            // the table one step ahead of its use
-            // (the unit entry point accepts samples beyond the table: those divisors are inverted here)
-            auto recip = [&](int k) { return k < NCB_KS_RTAB_SIZE ? __ldg(w.rtab + k) : __drcp_rn((double)k); };
-            const int k0 = i0 + jlo;
-            double rden = recip(k0);
+// ("outside the band"): they are reset at the end of the chunk before.  Lane 0 reads the ring a
+// step ahead (the slot was written in the chunk before; the last lane of this chunk writes
+// `rows - 1` columns behind, never the slot being read).
+template <int RING, bool IN_TABLE>
+__device__ __forceinline__ void warp_chunk(double *prev, const double *__restrict__ rtab, int lane, int rows,
+                                           int i0, int jlo, int jhi, int ng, int mg, int hh) {
+    constexpr int MASK = RING - 1;
+    WaveRow r;
+    wave_row_init(r, i0 + lane, lane, lane < rows, i0, jlo, jhi, ng, mg);
+    const int nsteps = (jhi - jlo) + rows - 1;
+    const int k0 = i0 + jlo;
+    const double *rp = rtab + k0;
+    double rden = IN_TABLE ? __ldg(rp) : wave_recip(rtab, k0);
+    const bool first = lane == 0, last = lane == rows - 1;
+    double up0 = first ? prev[r.j & MASK] : 1.0;
 #pragma unroll 1
-            for (int t = 0; t < nsteps; ++t) {
-                const double rden_next = recip(k0 + t + 1);
-                const double up_sh = __shfl_up_sync(0xffffffffu, cur, 1);
-                if (row_on && j >= jlo && j < jhi) {
-                    const double up = (lane == 0) ? prev[j & MASK] : up_sh;
-                    const int v = ngi - mg * j;
-                    double val = 1.0;
-                    if (abs(v) < hh)
-                        val = div_by_recip(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, dj)), den, rden);
-                    cur = val;
-                    left = val;
-                    if (lane == rows - 1) prev[j & MASK] = val;
-                }
-                ++j;
-                dj += 1.0;
-                den += 1.0;
-                rden = rden_next;
-            }
-            __syncwarp();
-        }
-        if (lane == 0) p_out[q] = clip01(prev[n & MASK]);
+    for (int t = 0; t < nsteps; ++t) {
+        const double rden_next = IN_TABLE ? __ldg(rp + t + 1) : wave_recip(rtab, k0 + t + 1);
+        double up0_next = 1.0;
+        if (first) up0_next = prev[(r.j + 1) & MASK];
+        const double up_sh = __shfl_up_sync(0xffffffffu, r.cur, 1);
+        const bool active = wave_cell(r, first ? up0 : up_sh, rden, hh);
+        if (last && active) prev[r.j & MASK] = r.cur;
+        wave_advance(r, mg);
+        rden = rden_next;
+        up0 = up0_next;
+    }
+}
+
+template <int RING>
+__device__ void warp_problem(double *prev, const double *__restrict__ rtab, int lane, const KsProblem &k,
+                             double *p_out_q) {
+    constexpr int MASK = RING - 1;
+    static_assert((RING & (RING - 1)) == 0, "ring size must be a power of two");
+    // every quantity below fits in 32 bits: n0 + n1 <= NCB_MAX_READS, so ng*i, mg*j and
+    // h <= lcm are at most 5120 * 5120
+    const int n = k.n, m = k.m;
+    const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
+    const int maxj0 = min((hh + mg - 1) / mg, n + 1);
+    const int fill = min(n + 1, RING);
+    for (int j = lane; j < fill; j += 32) prev[j] = (j < maxj0) ? 0.0 : 1.0;
+    __syncwarp();
+    int jhi_done = fill;                      // columns below this hold valid ring slots
+    const bool in_table = m + n + 2 < NCB_KS_RTAB_SIZE;
+    for (int i0 = 1; i0 <= m; i0 += 32) {
+        const int rows = min(32, m - i0 + 1);
+        const int ilast = i0 + rows - 1;
+        const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
+        const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);
+        const int jhi = min((ng * ilast + hh + mg - 1) / mg, n + 1);
+        // slots entering the band in this chunk that were last used RING columns ago
+        for (int j = jhi_done + lane; j < jhi; j += 32) prev[j & MASK] = 1.0;
+        jhi_done = max(jhi_done, jhi);
+        __syncwarp();
+        if (in_table) warp_chunk<RING, true>(prev, rtab, lane, rows, i0, jlo, jhi, ng, mg, hh);
+        else warp_chunk<RING, false>(prev, rtab, lane, rows, i0, jlo, jhi, ng, mg, hh);
         __syncwarp();
     }
+    if (lane == 0) *p_out_q = clip01(prev[n & MASK]);
+    __syncwarp();
 }
 
 // ---- CTA per problem: lockstep wavefront over THREADS rows ----------------------------------
 // The problems with the most band cells (a high-coverage position with a moderate shift: up to
 // 2 x 10^7 cells) would keep one warp busy for tens of milliseconds after everything else is
-// done; ks_scan_kernel hands those to this kernel.  Here THREADS rows advance together, thread r one column behind thread r - 1; the cell
-// above travels through a double-buffered shared-memory row (one barrier per step), the row
-// above the THREADS-row chunk is the full row `prev` (no wrap, so it never needs resetting: the
-// slots right of the band still hold the 1.0 of the initial fill).  Same cell arithmetic as the
-// other kernels, hence the same bits.
+// done; ks_scan_kernel hands those to the CTA form.  Here THREADS rows advance together, thread r
+// one column behind thread r - 1; the cell above travels through a double-buffered shared-memory
+// row (one barrier per step), the row above the THREADS-row chunk is the full row `prev` (no wrap,
+// so it never needs resetting: the slots right of the band still hold the 1.0 of the initial
+// fill).  Same cell arithmetic as the other kernels, hence the same bits.
+template <int THREADS, bool IN_TABLE>
+__device__ __forceinline__ void cta_chunk(double *prev, double *xbuf, const double *__restrict__ rtab, int tid,
+                                          int rows, int i0, int jlo, int jhi, int ng, int mg, int hh) {
+    WaveRow r;
+    wave_row_init(r, i0 + tid, tid, tid < rows, i0, jlo, jhi, ng, mg);
+    const int nsteps = (jhi - jlo) + rows - 1;
+    const int k0 = i0 + jlo;
+    const double *rp = rtab + k0;
+    double rden = IN_TABLE ? __ldg(rp) : wave_recip(rtab, k0);
+    const bool first = tid == 0, last = tid == rows - 1;
+    double up0 = first ? prev[r.j] : 1.0;
+    double *xw = xbuf + tid, *xr = xbuf + (first ? 0 : tid - 1);
+    int flip = 0;
+#pragma unroll 1
+    for (int t = 0; t < nsteps; ++t) {
+        const double rden_next = IN_TABLE ? __ldg(rp + t + 1) : wave_recip(rtab, k0 + t + 1);
+        xw[flip] = r.cur;               // the cell this row finished in the step before
+        double up0_next = 1.0;
+        if (first) up0_next = prev[min(r.j + 1, NCB_KS_RING_FULL - 1)];
+        __syncthreads();
+        const double up_x = xr[flip];
+        const bool active = wave_cell(r, first ? up0 : up_x, rden, hh);
+        if (last && active) prev[r.j] = r.cur;
+        wave_advance(r, mg);
+        rden = rden_next;
+        up0 = up0_next;
+        flip ^= THREADS;
+    }
+}
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-ks_cta_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out, NcbKsWork w, int kind) {
-    extern __shared__ double cta_smem[];   // prev[NCB_KS_RING_FULL], xbuf[2][THREADS]
-    double *prev = cta_smem;
-    double *xbuf = cta_smem + NCB_KS_RING_FULL;
+__device__ void cta_problem(double *prev, double *xbuf, const double *__restrict__ rtab, int tid,
+                            const KsProblem &k, double *p_out_q) {
+    const int n = k.n, m = k.m;
+    const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
+    const int maxj0 = min((hh + mg - 1) / mg, n + 1);
+    for (int j = tid; j <= n; j += THREADS) prev[j] = (j < maxj0) ? 0.0 : 1.0;
+    __syncthreads();
+    const bool in_table = m + n + 2 < NCB_KS_RTAB_SIZE;
+    for (int i0 = 1; i0 <= m; i0 += THREADS) {
+        const int rows = min(THREADS, m - i0 + 1);
+        const int ilast = i0 + rows - 1;
+        const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
+        const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);
+        const int jhi = min((ng * ilast + hh + mg - 1) / mg, n + 1);
+        if (in_table) cta_chunk<THREADS, true>(prev, xbuf, rtab, tid, rows, i0, jlo, jhi, ng, mg, hh);
+        else cta_chunk<THREADS, false>(prev, xbuf, rtab, tid, rows, i0, jlo, jhi, ng, mg, hh);
+        __syncthreads();
+    }
+    if (tid == 0) *p_out_q = clip01(prev[n]);
+    __syncthreads();   // prev is rewritten by the next problem
+}
+
+// ---- one launch for both forms ---------------------------------------------------------------
+// Every CTA first takes problems from the CTA queue (the HUGE bins, then the dearest LARGE ones,
+// a prefix of their cost-sorted list); when that queue is empty its warps turn to the warp queue.
+// The tail of the CTA phase on one SM overlaps the warp phase on the others -- as two launches on
+// one stream the two forms ran back to back, each with its own tail (24 % of the warp slots in
+// use on a high-coverage batch).
+template <int WARPS, int RING>
+__global__ void __launch_bounds__(WARPS * 32)
+ks_wave_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out, NcbKsWork w) {
+    extern __shared__ double wave_smem[];   // CTA form: prev[NCB_KS_RING_FULL], xbuf[2][THREADS]
+                                            // warp form: [WARPS][RING]
+    constexpr int THREADS = WARPS * 32;
     __shared__ int s_idx;
     const int tid = threadIdx.x;
-    // its problems: the HUGE bins, then the dearest LARGE ones (a prefix of their sorted list)
-    const int lo = w.hist[kind * NCB_KS_BUCKETS];
-    const int n_own = w.hist[(kind + 1) * NCB_KS_BUCKETS] - lo;
-    const int lo_large = w.hist[NCB_KS_KIND_LARGE * NCB_KS_BUCKETS];
-    const int n_all = n_own + w.fetch[NCB_KS_KINDS];
-    for (;;) {
-        if (tid == 0) s_idx = atomicAdd(&w.fetch[kind], 1);
-        __syncthreads();
-        const int idx = s_idx;
-        if (idx >= n_all) break;
-        const int q = w.list[idx < n_own ? lo + idx : lo_large + (idx - n_own)];
-        const KsProblem k = make_problem(n0[q], n1[q], h[q]);
-        const int n = k.n, m = k.m;
-        const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
-        const int maxj0 = min((hh + mg - 1) / mg, n + 1);
-        for (int j = tid; j <= n; j += THREADS) prev[j] = (j < maxj0) ? 0.0 : 1.0;
-        __syncthreads();
-        for (int i0 = 1; i0 <= m; i0 += THREADS) {
-            const int rows = min(THREADS, m - i0 + 1);
-            const int ilast = i0 + rows - 1;
-            const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
-            const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);
-            const int jhi = min((ng * ilast + hh + mg - 1) / mg, n + 1);
-            const int i = i0 + tid;
-            const bool row_on = tid < rows;
-            const double di = (double)i;
-            const int ngi = ng * i;
-            double left = 1.0, cur = 1.0;
-            const int nsteps = (jhi - jlo) + rows - 1;
-            int j = jlo - tid;
-            double dj = (double)j;
-            double den = (double)(i0 + jlo);
-            auto recip = [&](int kk) { return kk < NCB_KS_RTAB_SIZE ? __ldg(w.rtab + kk) : __drcp_rn((double)kk); };
-            const int k0 = i0 + jlo;
-            double rden = recip(k0);
-#pragma unroll 1
-            for (int t = 0; t < nsteps; ++t) {
-                const double rden_next = recip(k0 + t + 1);
-                double *xb = xbuf + (t & 1) * THREADS;
-                xb[tid] = cur;              // the cell this row finished in the step before
-                __syncthreads();
-                if (row_on && j >= jlo && j < jhi) {
-                    const double up = (tid == 0) ? prev[j] : xb[tid - 1];
-                    const int v = ngi - mg * j;
-                    double val = 1.0;
-                    if (abs(v) < hh)
-                        val = div_by_recip(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, dj)), den, rden);
-                    cur = val;
-                    left = val;
-                    if (tid == rows - 1) prev[j] = val;
-                }
-                ++j;
-                dj += 1.0;
-                den += 1.0;
-                rden = rden_next;
-            }
+    {
+        double *prev = wave_smem;
+        double *xbuf = wave_smem + NCB_KS_RING_FULL;
+        const int lo = w.hist[NCB_KS_KIND_HUGE * NCB_KS_BUCKETS];
+        const int n_own = w.hist[(NCB_KS_KIND_HUGE + 1) * NCB_KS_BUCKETS] - lo;
+        const int lo_large = w.hist[NCB_KS_KIND_LARGE * NCB_KS_BUCKETS];
+        const int n_all = n_own + w.fetch[NCB_KS_KINDS];
+        for (;;) {
+            if (tid == 0) s_idx = atomicAdd(&w.fetch[NCB_KS_KIND_HUGE], 1);
             __syncthreads();
+            const int idx = s_idx;
+            __syncthreads();               // s_idx is rewritten by the next fetch
+            if (idx >= n_all) break;
+            const int q = w.list[idx < n_own ? lo + idx : lo_large + (idx - n_own)];
+            cta_problem<THREADS>(prev, xbuf, w.rtab, tid, make_problem(n0[q], n1[q], h[q]), p_out + q);
         }
-        if (tid == 0) p_out[q] = clip01(prev[n]);
-        __syncthreads();   // s_idx and prev are rewritten by the next problem
+    }
+    {
+        const int lane = tid & 31;
+        double *prev = wave_smem + (size_t)(tid >> 5) * RING;
+        const int lo = w.hist[NCB_KS_KIND_LARGE * NCB_KS_BUCKETS] + w.fetch[NCB_KS_KINDS];   // the dearest went to the CTA form
+        const int hi = w.hist[(NCB_KS_KIND_LARGE + 1) * NCB_KS_BUCKETS];
+        for (;;) {
+            int idx = 0;
+            if (lane == 0) idx = lo + atomicAdd(&w.fetch[NCB_KS_KIND_LARGE], 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= hi) break;
+            const int q = w.list[idx];
+            warp_problem<RING>(prev, w.rtab, lane, make_problem(n0[q], n1[q], h[q]), p_out + q);
+        }
     }
 }
 
@@ -435,21 +533,18 @@ ks_cta_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_
 
 using namespace ncb;
 
-static const int KS_LARGE_WARPS = 8, KS_LARGE_BUF = NCB_KS_RING_SMALL;
-static const int KS_CTA_THREADS = 256;
-static const size_t KS_CTA_SMEM = (NCB_KS_RING_FULL + 2 * KS_CTA_THREADS) * sizeof(double);
+static const int KS_WAVE_WARPS = 8;
+static constexpr size_t KS_WAVE_SMEM_CTA = (NCB_KS_RING_FULL + 2 * KS_WAVE_WARPS * 32) * sizeof(double);
+static constexpr size_t KS_WAVE_SMEM_WARP = (size_t)KS_WAVE_WARPS * NCB_KS_RING_SMALL * sizeof(double);
+static constexpr size_t KS_WAVE_SMEM = KS_WAVE_SMEM_CTA > KS_WAVE_SMEM_WARP ? KS_WAVE_SMEM_CTA : KS_WAVE_SMEM_WARP;
+static const size_t KS_SMALL_SMEM = (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE + 8) * sizeof(double);
 
 int ncb_configure_ks_kernels(void) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(ks_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE + 8) * (int)sizeof(double));
+    e = cudaFuncSetAttribute(ks_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMALL_SMEM);
     if (e != cudaSuccess) return -1;
-    e = cudaFuncSetAttribute(ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             KS_LARGE_WARPS * KS_LARGE_BUF * (int)sizeof(double));
-    if (e != cudaSuccess) return -1;
-    e = cudaFuncSetAttribute(ks_cta_kernel<KS_CTA_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)KS_CTA_SMEM);
+    e = cudaFuncSetAttribute(ks_wave_kernel<KS_WAVE_WARPS, NCB_KS_RING_SMALL>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_WAVE_SMEM);
     if (e != cudaSuccess) return -1;
     return 0;
 }
@@ -469,15 +564,10 @@ int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, c
     ks_scan_kernel<<<1, NCB_KS_NBINS, 0, s>>>(w);
     ks_scatter_kernel<<<blocks, 256, 0, s>>>(nprob, w);
     // the long problems first: their warps are busy while the short kernels fill the rest
-    ks_cta_kernel<KS_CTA_THREADS><<<sm_count * 4, KS_CTA_THREADS, KS_CTA_SMEM, s>>>(
-        n0, n1, h, p_out, w, NCB_KS_KIND_HUGE);
-    ks_warp_kernel<KS_LARGE_WARPS, KS_LARGE_BUF, true>
-        <<<sm_count * 3, KS_LARGE_WARPS * 32, KS_LARGE_WARPS * KS_LARGE_BUF * sizeof(double), s>>>(
-            n0, n1, h, p_out, w, NCB_KS_KIND_LARGE);
+    ks_wave_kernel<KS_WAVE_WARPS, NCB_KS_RING_SMALL>
+        <<<sm_count * 3, KS_WAVE_WARPS * 32, KS_WAVE_SMEM, s>>>(n0, n1, h, p_out, w);
     int tblocks = (int)((nprob + KS_SMALL_THREADS - 1) / KS_SMALL_THREADS);
-    ks_small_kernel<<<tblocks, KS_SMALL_THREADS,
-                      (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE + 8) * sizeof(double), s>>>(
-        n0, n1, h, p_out, w);
+    ks_small_kernel<<<tblocks, KS_SMALL_THREADS, KS_SMALL_SMEM, s>>>(n0, n1, h, p_out, w);
     ks_equal_kernel<<<tblocks, KS_SMALL_THREADS, 0, s>>>(n0, h, p_out, w);
-    return cudaGetLastError() == cudaSuccess ? 7 : -1;
+    return cudaGetLastError() == cudaSuccess ? 6 : -1;
 }

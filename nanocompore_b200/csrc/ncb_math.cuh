@@ -277,8 +277,8 @@ NCB_HD inline double ks_prob_outside_square(long long n, long long h) {
 //     d <= 1/(2N): 1          1/(2N) < d <= 1/N: 1 - N! (2d - 1/N)^N        else: 1
 // (the third branch drops a term below 4e-13, checked against SciPy for every n that can
 // reach it; tests/test_math_host.py).
-NCB_HD inline double ks_equal_p(long long n, long long h) {
-    double p = ks_prob_outside_square(n, h);
+// `p` = 2 * the Horner product (ks_prob_outside_square, or a faster evaluation with the same bits)
+NCB_HD inline double ks_equal_finish(double p, long long n, long long h) {
     if (p >= 0.0 && p <= 1.0) return p;
     const double d = (double)h / (double)n;
     const double N = rint(0.5 * (double)n);
@@ -289,6 +289,9 @@ NCB_HD inline double ks_equal_p(long long n, long long h) {
         return clip01(1.0 - exp(lgamma(N + 1.0) + N * log(base)));
     }
     return 1.0;
+}
+NCB_HD inline double ks_equal_p(long long n, long long h) {
+    return ks_equal_finish(ks_prob_outside_square(n, h), n, h);
 }
 
 }  // namespace ncb

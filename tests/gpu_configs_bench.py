@@ -78,3 +78,11 @@ rng = np.random.default_rng(BASE_SEED + 5)
 high = [packed([make_transcript(rng, 250, 5000)]) for _ in range(2)]
 tail = [packed(make_skew_tail(rng, 25, n_positions=1000)) for _ in range(2)]
 run('config5 shard: 2 tx x 250 pos x 5000 reads/cond + 50 low-coverage tx x 1000 pos', high + tail, ('GMM', 'KS'), reps=2)
+# the same mix at the config's own proportions (1 high-coverage transcript per 25 of the tail) and
+# whole 1000-position transcripts: enough exact-KS problems of ~10^6 lattice cells to fill the GPU
+if '--large' in sys.argv:
+    rng = np.random.default_rng(BASE_SEED + 55)
+    high = [packed([make_transcript(rng, 1000, 5000)]) for _ in range(8)]
+    tail = [packed(make_skew_tail(rng, 25, n_positions=1000)) for _ in range(8)]
+    run('config5 shard at config proportions: 8 tx x 1000 pos x 5000 reads/cond + 200 low-coverage tx x 1000 pos',
+        [b for pair in zip(high, tail) for b in pair], ('GMM', 'KS'), reps=1)

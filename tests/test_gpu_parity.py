@@ -222,6 +222,28 @@ def test_ks_exact_pvalue_cta_class(engine_factory):
     assert np.array_equal(got, want)
 
 
+def test_ks_exact_pvalue_equal_sizes_large(engine_factory):
+    """Equal sample sizes up to the 5000-per-condition cap: the Horner product evaluated with table
+    reciprocals (ks_prob_outside_square_fast) has the bits of SciPy's divisions, down through the
+    denormal range and where the leading factor reaches zero."""
+    from oracle.ks_exact import ks_exact_p
+    eng = engine_factory(tests=('KS',))
+    rng = np.random.default_rng(12)
+    n = np.concatenate([rng.integers(2, 5121, size=300), [5120, 5000, 4999, 1, 2, 3, 4097]])
+    d = np.concatenate([rng.uniform(0.0, 0.75, size=300) ** 2, [0.4, 0.39, 0.001, 1.0, 0.5, 1.0, 0.3]])
+    h = np.clip(np.round(d * n).astype(np.int64), 1, n)
+    h[:20] = n[:20]                                  # h = n: every factor of the k = 1 block is <= 0
+    h[20:40] = np.maximum(n[20:40] // 2, 1)
+    got = eng.ks_exact_pvalues(n, n, h)
+    want = np.array([ks_exact_p(int(a), int(a), int(c)) for a, c in zip(n, h)])
+    assert ((want > 0) & (want < 1e-280)).sum() >= 3   # the true-division tail is exercised
+    assert np.array_equal(got, want)
+    # samples beyond the reciprocal table take the plain form
+    got = eng.ks_exact_pvalues([6000, 20000], [6000, 20000], [300, 700])
+    want = [ks_exact_p(6000, 6000, 300), ks_exact_p(20000, 20000, 700)]
+    assert np.array_equal(got, np.array(want))
+
+
 def test_bh_fdr_unit(engine_factory):
     from oracle.fdr import multipletests_filter_nan
     eng = engine_factory(tests=('KS',))
