@@ -18,12 +18,12 @@
 //   SMALL  window <= 64 cells: one thread per problem, its window in shared memory
 //          (interleaved by thread: conflict free); a warp holds problems of one cost bucket
 //   EQUAL  one thread per problem
-//   LARGE  one warp per problem: 32 rows advance together as a skewed wavefront (lane l is one
+//   LARGE  one warp per problem: 64 rows (two per lane) advance together as a skewed wavefront (lane l is two
 //          column behind lane l-1 and takes the cell above by shuffle); the row above the
-//          32-row chunk lives in a shared-memory ring.  Warps fetch problems from a counter,
+//          64-row chunk lives in a shared-memory ring.  Warps fetch problems from a counter,
 //          most expensive bucket first.
 //   HUGE   (a band too wide for the ring, plus the LARGE problems that alone would outlast the
-//          batch) one CTA per problem: 256 rows advance in lockstep, one barrier per step.
+//          batch) one CTA per problem: 512 rows advance in lockstep, one barrier per step.
 #include "ncb_internal.h"
 #include "ncb_math.cuh"
 
@@ -103,8 +103,8 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
                 long long maxj0 = min(ceildiv_ll(k.h, k.mg), (long long)k.n + 1);
                 long long lenA = min(2 * maxj0 + 2, (long long)k.n + 1);
                 double width = fmin(2.0 * (double)k.h / (double)k.mg + 1.0, (double)k.n + 1.0);
-                // columns a 32-row chunk of the wavefront touches, plus those entering next
-                double span = width + 2.0 * (32.0 * (double)k.ng / (double)k.mg) + 8.0;
+                // columns a 64-row chunk of the wavefront touches, plus those entering next
+                double span = width + 2.0 * (64.0 * (double)k.ng / (double)k.mg) + 8.0;
                 int kind;
                 // lenA < window: a row has at most lenA - 1 cells and the band moves by at most one
                 // column per row, so the thread kernel never reads past its window
@@ -314,39 +314,74 @@ __global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_o
 // v = ng i - mg j (inside the band iff |v| < h).  The step is branch free: every lane computes,
 // the selects decide what is kept (outside the band a cell is 1, outside the chunk's column range
 // nothing changes).
-struct WaveRow {
-    double di, dj, den, left, cur;
-    int j, jr, v;            // column, column - jlo, ng i - mg j
-    unsigned span;           // jhi - jlo for a live row, 0 for a row past the last one
+// The rings are addressed with 32-bit shared-window addresses computed once per problem: through a
+// generic pointer the compiler rebuilt the window base (S2R SR_CgaCtaId, shifts, adds) next to every
+// predicated access, 14 of the 51 instructions of a step.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// Two rows per thread: thread r of a chunk holds rows a = 2 r and b = 2 r + 1.  Row rho is at
+// column jlo - rho + t at step t, so b runs one column behind a and takes the cell above from
+// a's value of the step before -- the two cells of a step are independent of each other (two
+// chains to interleave), share the divisor i + j and its reciprocal, the loop, the exchange with
+// the neighbouring thread and the table / ring reads: 22 instead of 37 instructions per 32 cells.
+struct WavePair {
+    double di_a, di_b, dj_a, dj_b, den, a, b;   // a, b: the rows' latest cells (also their `left`)
+    int j, jr, va, vb;      // a's column, a's column - jlo, band coordinates ng i - mg j + h - 1
+                            // (a cell is inside the band iff 0 <= v < 2 h - 1); b is at column j - 1
+    unsigned span_a, span_b; // jhi - jlo for a live row, 0 for a row past the last one
+    unsigned keep_a, keep_b; // the same for the chunk's last row (its cells go to the row buffer), else 0
 };
+// (the compiler otherwise re-derives "is this row live / the last one" from the lane index in
+// every step instead of keeping the folded bound in a register)
+__device__ __forceinline__ unsigned opaque(unsigned x) {
+    asm volatile("" : "+r"(x));
+    return x;
+}
 
-__device__ __forceinline__ void wave_row_init(WaveRow &r, int i, int r_idx, bool on, int i0, int jlo, int jhi,
-                                              int ng, int mg) {
-    r.di = (double)i;
-    r.j = jlo - r_idx;
-    r.jr = -r_idx;
-    r.dj = (double)r.j;
+__device__ __forceinline__ void wave_pair_init(WavePair &r, int r_idx, int rows, int i0, int jlo, int jhi,
+                                               int ng, int mg, int hh) {
+    const int ia = i0 + 2 * r_idx;
+    r.di_a = (double)ia;
+    r.di_b = (double)(ia + 1);
+    r.j = jlo - 2 * r_idx;
+    r.jr = -2 * r_idx;
+    r.dj_a = (double)r.j;
+    r.dj_b = (double)(r.j - 1);
     r.den = (double)(i0 + jlo);
-    r.v = ng * i - mg * r.j;
-    r.span = on ? (unsigned)(jhi - jlo) : 0u;
-    r.left = 1.0;
-    r.cur = 1.0;
+    r.va = ng * ia - mg * r.j + hh - 1;
+    r.vb = ng * (ia + 1) - mg * (r.j - 1) + hh - 1;
+    r.span_a = opaque(2 * r_idx < rows ? (unsigned)(jhi - jlo) : 0u);
+    r.span_b = opaque(2 * r_idx + 1 < rows ? (unsigned)(jhi - jlo) : 0u);
+    r.keep_a = opaque(2 * r_idx == rows - 1 ? (unsigned)(jhi - jlo) : 0u);
+    r.keep_b = opaque(2 * r_idx + 1 == rows - 1 ? (unsigned)(jhi - jlo) : 0u);
+    r.a = 1.0;
+    r.b = 1.0;
 }
 
-// the cell of this step from `up` (cell above) and r.left; returns true if the row is inside the
-// chunk's column range (then r.cur / r.left hold the new cell)
-__device__ __forceinline__ bool wave_cell(WaveRow &r, double up, double rden, int hh) {
-    const bool active = (unsigned)r.jr < r.span;
-    const bool inside = (unsigned)(r.v + hh - 1) < (unsigned)(2 * hh - 1);
-    const double val = div_by_recip(NCB_DADD(NCB_DMUL(up, r.di), NCB_DMUL(r.left, r.dj)), r.den, rden);
-    const double x = inside ? val : 1.0;
-    r.cur = active ? x : r.cur;
-    r.left = r.cur;
-    return active;
+// the two cells of this step; `up` = the cell above row a (row b of the thread before, one step
+// ago).  Returns through act_a / act_b whether the rows are inside the chunk's column range.
+__device__ __forceinline__ void wave_pair_cells(WavePair &r, double up, double rden, int hh, bool &act_a, bool &act_b) {
+    act_a = (unsigned)r.jr < r.span_a;
+    act_b = (unsigned)(r.jr - 1) < r.span_b;
+    const unsigned lim = (unsigned)(2 * hh - 1);
+    const bool in_a = (unsigned)r.va < lim, in_b = (unsigned)r.vb < lim;
+    const double val_b = div_by_recip(NCB_DADD(NCB_DMUL(r.a, r.di_b), NCB_DMUL(r.b, r.dj_b)), r.den, rden);
+    const double val_a = div_by_recip(NCB_DADD(NCB_DMUL(up, r.di_a), NCB_DMUL(r.a, r.dj_a)), r.den, rden);
+    const double xb = in_b ? val_b : 1.0, xa = in_a ? val_a : 1.0;
+    r.b = act_b ? xb : r.b;
+    r.a = act_a ? xa : r.a;
 }
-__device__ __forceinline__ void wave_advance(WaveRow &r, int mg) {
-    ++r.j; ++r.jr; r.v -= mg;
-    r.dj += 1.0; r.den += 1.0;
+__device__ __forceinline__ void wave_pair_advance(WavePair &r, int mg) {
+    ++r.j; ++r.jr; r.va -= mg; r.vb -= mg;
+    r.dj_a += 1.0; r.dj_b += 1.0; r.den += 1.0;
 }
 
 // reciprocal of k: from the table, or (unit entry point, samples beyond the table) computed
@@ -354,8 +389,8 @@ __device__ __forceinline__ double wave_recip(const double *__restrict__ rtab, in
     return k < NCB_KS_RTAB_SIZE ? __ldg(rtab + k) : __drcp_rn((double)k);
 }
 
-// ---- warp per problem: skewed wavefront over 32 rows --------------------------------------
-// The row above the current 32-row chunk lives in a power-of-two ring of RING doubles indexed
+// ---- warp per problem: skewed wavefront over 64 rows --------------------------------------
+// The row above the current 64-row chunk lives in a power-of-two ring of RING doubles indexed
 // by j & (RING - 1).  The band moves to the right, so a slot is reused only by columns RING
 // apart; classification guarantees RING >= the widest span a chunk touches (or RING > n, in
 // which case the ring never wraps).  Slots that enter the band for the first time must read 1
@@ -366,23 +401,26 @@ template <int RING, bool IN_TABLE>
 __device__ __forceinline__ void warp_chunk(double *prev, const double *__restrict__ rtab, int lane, int rows,
                                            int i0, int jlo, int jhi, int ng, int mg, int hh) {
     constexpr int MASK = RING - 1;
-    WaveRow r;
-    wave_row_init(r, i0 + lane, lane, lane < rows, i0, jlo, jhi, ng, mg);
+    WavePair r;
+    wave_pair_init(r, lane, rows, i0, jlo, jhi, ng, mg, hh);
     const int nsteps = (jhi - jlo) + rows - 1;
     const int k0 = i0 + jlo;
     const double *rp = rtab + k0;
     double rden = IN_TABLE ? __ldg(rp) : wave_recip(rtab, k0);
-    const bool first = lane == 0, last = lane == rows - 1;
-    double up0 = first ? prev[r.j & MASK] : 1.0;
-#pragma unroll 1
+    const bool first = lane == 0;
+    const unsigned base = smem_addr(prev);
+    double up0 = first ? lds_f64(base + 8u * (unsigned)(r.j & MASK)) : 1.0;
+#pragma unroll 2
     for (int t = 0; t < nsteps; ++t) {
         const double rden_next = IN_TABLE ? __ldg(rp + t + 1) : wave_recip(rtab, k0 + t + 1);
         double up0_next = 1.0;
-        if (first) up0_next = prev[(r.j + 1) & MASK];
-        const double up_sh = __shfl_up_sync(0xffffffffu, r.cur, 1);
-        const bool active = wave_cell(r, first ? up0 : up_sh, rden, hh);
-        if (last && active) prev[r.j & MASK] = r.cur;
-        wave_advance(r, mg);
+        if (first) up0_next = lds_f64(base + 8u * (unsigned)((r.j + 1) & MASK));
+        const double up_sh = __shfl_up_sync(0xffffffffu, r.b, 1);
+        bool act_a, act_b;
+        wave_pair_cells(r, first ? up0 : up_sh, rden, hh, act_a, act_b);
+        if ((unsigned)r.jr < r.keep_a) sts_f64(base + 8u * (unsigned)(r.j & MASK), r.a);
+        if ((unsigned)(r.jr - 1) < r.keep_b) sts_f64(base + 8u * (unsigned)((r.j - 1) & MASK), r.b);
+        wave_pair_advance(r, mg);
         rden = rden_next;
         up0 = up0_next;
     }
@@ -403,8 +441,8 @@ __device__ void warp_problem(double *prev, const double *__restrict__ rtab, int 
     __syncwarp();
     int jhi_done = fill;                      // columns below this hold valid ring slots
     const bool in_table = m + n + 2 < NCB_KS_RTAB_SIZE;
-    for (int i0 = 1; i0 <= m; i0 += 32) {
-        const int rows = min(32, m - i0 + 1);
+    for (int i0 = 1; i0 <= m; i0 += 64) {
+        const int rows = min(64, m - i0 + 1);
         const int ilast = i0 + rows - 1;
         const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
         const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);
@@ -421,10 +459,10 @@ __device__ void warp_problem(double *prev, const double *__restrict__ rtab, int 
     __syncwarp();
 }
 
-// ---- CTA per problem: lockstep wavefront over THREADS rows ----------------------------------
+// ---- CTA per problem: lockstep wavefront over 2 x THREADS rows ------------------------------
 // The problems with the most band cells (a high-coverage position with a moderate shift: up to
 // 2 x 10^7 cells) would keep one warp busy for tens of milliseconds after everything else is
-// done; ks_scan_kernel hands those to the CTA form.  Here THREADS rows advance together, thread r
+// done; ks_scan_kernel hands those to the CTA form.  Here 2 x THREADS rows advance together, thread r
 // one column behind thread r - 1; the cell above travels through a double-buffered shared-memory
 // row (one barrier per step), the row above the THREADS-row chunk is the full row `prev` (no wrap,
 // so it never needs resetting: the slots right of the band still hold the 1.0 of the initial
@@ -432,31 +470,39 @@ __device__ void warp_problem(double *prev, const double *__restrict__ rtab, int 
 template <int THREADS, bool IN_TABLE>
 __device__ __forceinline__ void cta_chunk(double *prev, double *xbuf, const double *__restrict__ rtab, int tid,
                                           int rows, int i0, int jlo, int jhi, int ng, int mg, int hh) {
-    WaveRow r;
-    wave_row_init(r, i0 + tid, tid, tid < rows, i0, jlo, jhi, ng, mg);
+    WavePair r;
+    wave_pair_init(r, tid, rows, i0, jlo, jhi, ng, mg, hh);
     const int nsteps = (jhi - jlo) + rows - 1;
     const int k0 = i0 + jlo;
     const double *rp = rtab + k0;
     double rden = IN_TABLE ? __ldg(rp) : wave_recip(rtab, k0);
-    const bool first = tid == 0, last = tid == rows - 1;
-    double up0 = first ? prev[r.j] : 1.0;
-    double *xw = xbuf + tid, *xr = xbuf + (first ? 0 : tid - 1);
-    int flip = 0;
-#pragma unroll 1
-    for (int t = 0; t < nsteps; ++t) {
+    const bool first = tid == 0;
+    const unsigned base = smem_addr(prev);
+    double up0 = first ? lds_f64(base + 8u * (unsigned)r.j) : 1.0;
+    const unsigned xw = smem_addr(xbuf + tid), xr = smem_addr(xbuf + (first ? 0 : tid - 1));
+    // one step; `off` selects the half of the double buffer (a compile-time constant per call site)
+    auto step = [&](const unsigned off, const int t) {
         const double rden_next = IN_TABLE ? __ldg(rp + t + 1) : wave_recip(rtab, k0 + t + 1);
-        xw[flip] = r.cur;               // the cell this row finished in the step before
+        sts_f64(xw + off, r.b);         // the cell row b finished in the step before
         double up0_next = 1.0;
-        if (first) up0_next = prev[min(r.j + 1, NCB_KS_RING_FULL - 1)];
+        if (first) up0_next = lds_f64(base + 8u * (unsigned)min(r.j + 1, NCB_KS_RING_FULL - 1));
         __syncthreads();
-        const double up_x = xr[flip];
-        const bool active = wave_cell(r, first ? up0 : up_x, rden, hh);
-        if (last && active) prev[r.j] = r.cur;
-        wave_advance(r, mg);
+        const double up_x = lds_f64(xr + off);
+        bool act_a, act_b;
+        wave_pair_cells(r, first ? up0 : up_x, rden, hh, act_a, act_b);
+        if ((unsigned)r.jr < r.keep_a) sts_f64(base + 8u * (unsigned)r.j, r.a);
+        if ((unsigned)(r.jr - 1) < r.keep_b) sts_f64(base + 8u * (unsigned)(r.j - 1), r.b);
+        wave_pair_advance(r, mg);
         rden = rden_next;
         up0 = up0_next;
-        flip ^= THREADS;
+    };
+    int t = 0;
+#pragma unroll 1
+    for (; t + 1 < nsteps; t += 2) {
+        step(0u, t);
+        step(8u * THREADS, t + 1);
     }
+    if (t < nsteps) step(0u, t);
 }
 
 template <int THREADS>
@@ -468,8 +514,8 @@ __device__ void cta_problem(double *prev, double *xbuf, const double *__restrict
     for (int j = tid; j <= n; j += THREADS) prev[j] = (j < maxj0) ? 0.0 : 1.0;
     __syncthreads();
     const bool in_table = m + n + 2 < NCB_KS_RTAB_SIZE;
-    for (int i0 = 1; i0 <= m; i0 += THREADS) {
-        const int rows = min(THREADS, m - i0 + 1);
+    for (int i0 = 1; i0 <= m; i0 += 2 * THREADS) {
+        const int rows = min(2 * THREADS, m - i0 + 1);
         const int ilast = i0 + rows - 1;
         const int a0 = ng * i0 - hh;            // floor(a0 / mg) + 1, clamped to [0, n]
         const int jlo = min(max((a0 >= 0 ? a0 / mg : -((-a0 + mg - 1) / mg)) + 1, 0), n);

@@ -222,6 +222,35 @@ def test_ks_exact_pvalue_cta_class(engine_factory):
     assert np.array_equal(got, want)
 
 
+def test_ks_exact_pvalue_wavefront_edges(engine_factory):
+    """The wavefront forms on chunk edges: m a multiple of 32 / 256, one row left over, bands narrower
+    than a chunk and wider than the warp form's ring -- bitwise SciPy's compiled recurrence.
+    Submitted alone (each problem is then among the dearest of its batch: CTA form) and 400 at once
+    (the queue hands several problems to every CTA and warp)."""
+    from scipy.stats._stats_py import _compute_outer_prob_inside_method
+    eng = engine_factory(tests=('KS',))
+    shapes = [(4128, 40, 0.5), (4129, 37, 0.45), (4127, 41, 0.6), (5121, 5119, 0.25), (5100, 4999, 0.28),
+              (4096, 31, 0.9), (6000, 23, 0.8), (9000, 1240, 0.3), (2049, 2047, 0.3), (5119, 64, 0.7)]
+    for rep in range(2):
+        for a, b, d in shapes:
+            n0, n1 = (a, b) if rep == 0 else (b, a)
+            g = int(np.gcd(n0, n1))
+            lcm = n0 // g * n1
+            h = max(1, round(d * lcm))
+            cells = max(n0, n1) * min(2.0 * h / (max(n0, n1) // g) + 1, min(n0, n1) + 1)
+            assert cells >= 131072, (a, b, d, cells)
+            got = eng.ks_exact_pvalues([n0], [n1], [h])
+            want = min(max(_compute_outer_prob_inside_method(n0, n1, g, h), 0.0), 1.0)
+            assert got[0] == want, (n0, n1, h, got[0], want)
+    n0 = np.array([a for a, _, _ in shapes] * 40, dtype=np.int32)
+    n1 = np.array([b for _, b, _ in shapes] * 40, dtype=np.int32)
+    g = np.gcd(n0, n1)
+    lcm = n0.astype(np.int64) // g * n1
+    h = np.array([max(1, round(d * l)) for (_, _, d), l in zip(shapes * 40, lcm)], dtype=np.int64)
+    got = eng.ks_exact_pvalues(n0, n1, h)
+    assert np.array_equal(got[:10], got[-10:]) and np.array_equal(got.reshape(40, 10), np.tile(got[:10], (40, 1)))
+
+
 def test_ks_exact_pvalue_equal_sizes_large(engine_factory):
     """Equal sample sizes up to the 5000-per-condition cap: the Horner product evaluated with table
     reciprocals (ks_prob_outside_square_fast) has the bits of SciPy's divisions, down through the
