@@ -534,8 +534,11 @@ __device__ void cta_problem(double *prev, double *xbuf, const double *__restrict
 // The tail of the CTA phase on one SM overlaps the warp phase on the others -- as two launches on
 // one stream the two forms ran back to back, each with its own tail (24 % of the warp slots in
 // use on a high-coverage batch).
+#ifndef KS_WAVE_MINB
+#define KS_WAVE_MINB 3   /* 74 registers, no spills (64 with 4): -2 % */
+#endif
 template <int WARPS, int RING>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, KS_WAVE_MINB)
 ks_wave_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out, NcbKsWork w) {
     extern __shared__ double wave_smem[];   // CTA form: prev[NCB_KS_RING_FULL], xbuf[2][THREADS]
                                             // warp form: [WARPS][RING]

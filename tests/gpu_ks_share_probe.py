@@ -3,7 +3,7 @@ on exact-KS problem sets of high-coverage shards; tuning helper.  Measured: 3072
 32768 lose 15-45 %."""
 import glob, json, os, sys, time
 import numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nanocompore_b200 import _lib as L
 from nanocompore_b200.engine import Engine, pack_csr
 from nanocompore_b200.synthetic import make_transcript, BASE_SEED
@@ -21,7 +21,7 @@ for reads, npos in ((5000, 250), (5000, 2500), (1000, 400)):
     sets[(reads, npos)] = (n0[ok], n1[ok], h[ok])
     eng.close()
     del batch
-for lib in sorted(glob.glob('/root/repo/build/tune/share*.so')):
+for lib in sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'build', 'tune', 'share*.so'))):
     eng = Engine(0, tests=('KS',), lib_path=lib)
     out = {}
     for key, (n0, n1, h) in sets.items():
