@@ -317,7 +317,12 @@ __global__ void ks_equal_kernel(const int32_t *n0, const int64_t *h, double *p_o
 // The rings are addressed with 32-bit shared-window addresses computed once per problem: through a
 // generic pointer the compiler rebuilt the window base (S2R SR_CgaCtaId, shifts, adds) next to every
 // predicated access, 14 of the 51 instructions of a step.
-__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// (opaque: the compiler otherwise treats the address as rematerialisable and rebuilds it at every use)
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
 __device__ __forceinline__ double lds_f64(unsigned addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
