@@ -13,10 +13,18 @@ import torch
 import torch.distributed as dist
 
 
-def work_estimate(n_positions, reads_per_position, gmm=True):
-    """Relative cost of a transcript: positions x reads x (sort/statistics + EM)."""
+def work_estimate(n_positions, reads_per_position, gmm=True, ks=True):
+    """Relative cost of a transcript: positions x reads x (sort/statistics + EM + exact KS).
+
+    The exact KS p-value walks a lattice band of ~n0 x 2 D n1 cells, and D shrinks like
+    1 / sqrt(n) under the null: its cost per read grows like sqrt(reads) and takes over at high
+    coverage.  The weights are fitted to the measured device time per position at 200 reads
+    (33 ns, BASELINE config 3) and at 10 000 reads (8.6 us, the 5 000-per-condition positions of
+    config 5): a ratio of 260, where reads x log(reads) alone predicts 55."""
     n = np.asarray(reads_per_position, dtype=np.float64)
     per_read = 1.0 + (8.0 if gmm else 0.0) + 0.2 * np.log2(np.maximum(n, 2.0))
+    if ks:
+        per_read = per_read + 1.6 * np.sqrt(n)
     return np.asarray(n_positions, dtype=np.float64) * n * per_read
 
 
