@@ -1,5 +1,7 @@
 """High-coverage positions (BASELINE config 5: 5000 reads/condition): where the time goes, and the
-rate of the exact-KS wavefront kernels in lattice cells per second.  Tuning helper, not a test."""
+rate of the exact-KS wavefront kernels in lattice cells per second.  Tuning helper, not a test.
+
+    python tests/gpu_ks_highcov_probe.py [transcripts] [reads per condition] [positions per transcript]"""
 import json, os, sys, time
 import numpy as np
 import torch
@@ -9,8 +11,10 @@ from nanocompore_b200.engine import Engine, Results, pack_csr
 from nanocompore_b200.synthetic import make_transcript, BASE_SEED
 
 n_tx = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+reads = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+n_pos = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 rng = np.random.default_rng(BASE_SEED + 5)
-txs = [make_transcript(rng, 1000, 5000) for _ in range(n_tx)]
+txs = [make_transcript(rng, n_pos, reads) for _ in range(n_tx)]
 batch = pack_csr([(t.data, t.samples, t.conditions) for t in txs])[0].to('cuda')
 eng = Engine(0, tests=('GMM', 'KS'), min_coverage=30, dwell_is_raw=True)
 res = Results(batch.n_positions, 4, torch.device('cuda'), diagnostics=True)
@@ -41,7 +45,7 @@ t_unit = time.perf_counter() - t0
 t0 = time.perf_counter()
 p = eng.ks_exact_pvalues(n0.astype(np.int32), n1.astype(np.int32), h)
 t_unit = time.perf_counter() - t0
-print(json.dumps(dict(positions=batch.n_positions, entries=batch.n_entries,
+print(json.dumps(dict(reads_per_condition=reads, positions=batch.n_positions, entries=batch.n_entries,
                       ms_stats=t['ms_stats'] / nb, ms_gmm=t['ms_gmm'] / nb, ms_ks=t['ms_ks'] / nb,
                       problems=int(ok.sum()), equal_sizes=int(((n0 == n1) & (n0 > 0)).sum()),
                       skipped_underflow=int(skipped.sum()), walked=int(cells.size),

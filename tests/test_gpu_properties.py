@@ -211,3 +211,35 @@ def test_depleted_condition_flips_mod_cluster(engine_factory):
         std, _, _, _ = ostats.outlier_standardise(data[ok])
     want = gmm_test_split(ostats.outlier_standardise(data[ok])[0], samples, conditions, SAMPLE_IDS, 1, 'hard')
     assert_equal_nan(b['counts'][0, 0][ok].astype(np.uint32), want['kd1_mod'], 'kd1_mod with depleted = wt')
+
+
+def test_pipelined_engines_match_a_single_engine(engine_factory):
+    """What bench.py and readers.TranscriptPipeline do: batches issued round-robin on several
+    engines / streams (each engine forks its exact-KS kernels to an auxiliary stream), host batches
+    and device batches mixed.  Every result column must be bitwise what one engine gives when it
+    runs the batches one after the other -- the schedule must not leak into the results."""
+    from nanocompore_b200.engine import Results
+    opts = dict(tests=('GMM', 'KS', 'MW', 'TT'), min_coverage=30, dwell_is_raw=True, with_logit=True)
+    rng = np.random.default_rng(BASE_SEED + 77)
+    batches = []
+    for b in range(8):
+        txs = [make_transcript(rng, 400, int(n)) for n in rng.integers(40, 140, size=6)]
+        batches.append(pack_csr([(t.data, t.samples, t.conditions) for t in txs], pin=True)[0])
+    ref_engine = engine_factory(**opts)
+    want = [ref_engine.compare_csr(b.to('cuda')).numpy() for b in batches]
+    engines = [engine_factory(**opts) for _ in range(4)]
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    results = [Results(b.n_positions, 4, None if i % 2 else torch.device('cuda')) for i, b in enumerate(batches)]
+    for rep in range(2):                      # the second round reuses warm buffers in another order
+        order = range(8) if rep == 0 else reversed(range(8))
+        for i in order:
+            s = i % 4
+            src = batches[i] if i % 2 else batches[i].to('cuda')
+            engines[s].compare_csr(src, results[i], stream=streams[s], wait=False)
+        for s in range(4):
+            engines[s].wait(streams[s])
+        torch.cuda.synchronize()
+        for i in range(8):
+            got = results[i].numpy()
+            for key in ('status', 'pvalues', 'stats', 'counts'):
+                assert_equal_nan(got[key], want[i][key], f'batch {i} {key}')
