@@ -46,10 +46,11 @@ struct NcbDeviceArgs {
 //   class 3   : one 128-thread CTA per position, 8 entries per thread (a 256-thread CTA spends the EM
 //               iteration of a 600-read position in its block-wide reduction: 4.4x the cost of 300 reads)
 //   class 4   : one 256-thread CTA per position, 8 entries per thread
-//   class 5   : one 1024-thread CTA per position, 10 entries per thread
-enum { NCB_NUM_CLASSES = 6, NCB_NUM_PHASES = 4 };   // phases: statistics / mixture, 2 / 3 variables
+//   class 5   : one 512-thread CTA per position, 8 entries per thread
+//   class 6   : one 1024-thread CTA per position, 10 entries per thread
+enum { NCB_NUM_CLASSES = 7, NCB_NUM_PHASES = 4 };   // phases: statistics / mixture, 2 / 3 variables
 #define NCB_WL_COUNTERS (NCB_NUM_CLASSES * (1 + NCB_NUM_PHASES))
-static const int NCB_CLASS_CAP[NCB_NUM_CLASSES] = {128, 256, 512, 1024, 2048, NCB_MAX_READS};
+static const int NCB_CLASS_CAP[NCB_NUM_CLASSES] = {128, 256, 512, 1024, 2048, 4096, NCB_MAX_READS};
 
 // worklists: class_count[c] positions in class_list[c * P ...]
 struct NcbWorklists {

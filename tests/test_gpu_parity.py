@@ -167,13 +167,14 @@ def test_tiny_coverage_fixture_like(engine_factory, n):
 
 
 @pytest.mark.parametrize('n,cls', [(200, 'warp16'), (300, 'cta128'), (505, 'cta128'), (700, 'cta256'),
-                                   (2600, 'cta1024')])
+                                   (1100, 'cta512'), (2040, 'cta512'), (2600, 'cta1024')])
 def test_large_size_classes(engine_factory, n, cls):
     eng = engine_factory(tests=ALL_TESTS, with_logit=False, min_coverage=0)
     P = 12 if n > 1000 else 24
     data, samples, conditions, _ = prepared(900 + n, P, n, quantised=(n in (505, 700)))
     assert {'warp16': 256 < data.shape[1] <= 512, 'cta128': 512 < data.shape[1] <= 1024,
-            'cta256': 1024 < data.shape[1] <= 2048, 'cta1024': data.shape[1] > 2048}[cls]
+            'cta256': 1024 < data.shape[1] <= 2048, 'cta512': 2048 < data.shape[1] <= 4096,
+            'cta1024': data.shape[1] > 4096}[cls]
     res = run_dense(eng, data, samples, conditions)
     check_against_oracle(res, data, samples, conditions, with_logit=False)
 
