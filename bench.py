@@ -16,7 +16,8 @@ Printed JSON (one line, rank 0):
             batches issued round-robin on ``--slots`` engines/streams
   e2e       positions/s through the public API with pinned HOST batches: H2D copy of the reads,
             kernels and D2H copy of the result columns inside the timed region (``--slots`` engines on
-            as many streams so that the copies of one batch overlap the kernels of the others)
+            as many streams so that the copies of one batch overlap the kernels of the others); wall
+            clock, K steps timed three times over the same batches, the median pass reported
   roofline  HBM roofline of the dominant kernel (position kernel), live CUDA-event timing
   cpu_baseline  the oracle port (oracle/comparator.py: numpy + SciPy per position, as the
             reference does) on one host core, on a bounded sample of the same workload
@@ -324,23 +325,31 @@ def run_gpu_arm(args):
     gc.disable()            # a collection inside the wall-clock region would be charged to the path
     for b in range(W):
         engines[b % NSLOT].compare_csr(host_batches[b], res_host[b % NSLOT], stream=streams[b % NSLOT], wait=False)
-    barrier()
-    t0 = time.perf_counter()
-    tested_host = 0
-    pending = [None] * NSLOT
-    for i, b in enumerate(range(W, n_batches)):
-        s = i % NSLOT
-        if pending[s] is not None:
-            engines[s].wait(streams[s])
-            tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
-        engines[s].compare_csr(host_batches[b], res_host[s], stream=streams[s], wait=False)
-        pending[s] = b
-    for s in range(NSLOT):
-        if pending[s] is not None:
-            engines[s].wait(streams[s])
-            tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
-    torch.cuda.synchronize(dev)
-    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+    # the wall-clock region is short (K steps = tens of milliseconds) and a single stall of the host
+    # (the nvidia-smi sampler attaching, a neighbour on the box) has been seen to triple it: the K
+    # steps are timed E2E_REPEATS times over the same batches and the MEDIAN pass is reported; every
+    # pass is listed in the JSON line
+    E2E_REPEATS = 3
+    e2e_passes = []
+    for _ in range(E2E_REPEATS):
+        barrier()
+        t0 = time.perf_counter()
+        tested_host = 0
+        pending = [None] * NSLOT
+        for i, b in enumerate(range(W, n_batches)):
+            s = i % NSLOT
+            if pending[s] is not None:
+                engines[s].wait(streams[s])
+                tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
+            engines[s].compare_csr(host_batches[b], res_host[s], stream=streams[s], wait=False)
+            pending[s] = b
+        for s in range(NSLOT):
+            if pending[s] is not None:
+                engines[s].wait(streams[s])
+                tested_host += int(((res_host[s].status & L.NCB_POS_DROP_MASK) == 0).sum())
+        torch.cuda.synchronize(dev)
+        e2e_passes.append(max_over_ranks((time.perf_counter() - t0) * 1000.0))
+    ms_e2e = float(np.median(e2e_passes))
     gc.enable()
     clocks = sampler.stop()
     total_tested_host = sum_over_ranks(float(tested_host))
@@ -438,7 +447,8 @@ def run_gpu_arm(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / K},
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / K,
+                "passes_ms_per_step": [m / K for m in e2e_passes], "reported": "median pass"},
         "gpu_launches": total_launches,
         "final_gather": gathered,
         "clocks": clocks,
