@@ -46,6 +46,9 @@ __device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   //
 #define KS_CTA_SHARE 3072.0
 #endif
 #define KS_CTA_MIN_CELLS 131072.0
+#ifndef KS_USE_STRIP
+#define KS_USE_STRIP 1    /* 0: narrow bands stay on the chunked warp form (A/B builds) */
+#endif
 #define KS_SMALL_MAX_CELLS 16384.0   /* band cells a single thread may walk (~0.4 ms) */
 
 struct KsProblem {
@@ -464,6 +467,102 @@ __device__ void warp_problem(double *prev, const double *__restrict__ rtab, int 
     __syncwarp();
 }
 
+// ---- warp per problem, narrow bands: lanes own columns ------------------------------------------
+// A chunked wavefront keeps its lanes busy w / (w + rows + drift) of the time: 55 % for the median
+// band of a 5000-read position (155 columns), because every 64-row chunk starts and drains at the
+// band's edges.  Here lane l owns the C columns [l C, l C + C) of the band RELATIVE to its left
+// edge, for every row, and runs l rows behind lane l - 1: in period p it computes its strip of row
+// i = p - l + 1, one cell per step, so apart from the first and last 31 periods of a problem every
+// lane computes a cell in every step.  The band's left edge moves by s = 0 or 1 columns per row,
+// so the cell above relative column r is relative column r + s of the row before: the lane's own
+// previous strip (registers), and for the last column of a strip with s = 1 the FIRST column of
+// lane l + 1's strip of that row -- which lane l + 1 computes in the first step of the same
+// period (shuffle after that step).  The cell to the left of a strip's first column is the last
+// column of lane l - 1's strip of the same row, finished in the step before the period starts.
+// Rows carry their exact band limits ((quotient, remainder) pairs, no division), so there is no
+// in-band test, and outside the band a cell above reads as 1.  Same cell arithmetic as the other
+// forms, hence the same bits (schedule checked against the oracle by a lane-level emulation).
+template <int C>
+__device__ void strip_problem(const double *__restrict__ rtab, int lane, const KsProblem &k, double *p_out_q) {
+    const int n = k.n, m = k.m;
+    const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
+    double U[C], V[C];          // the strip of the row before / of the current row
+#pragma unroll
+    for (int q = 0; q < C; ++q) { U[q] = 0.0; V[q] = 0.0; }      // row 0: 0 inside the band
+    int prev_min = 0, prev_w = min((hh + mg - 1) / mg, n + 1);    // row 0: [0, maxj0)
+    // band of row i: minj = floor((ng i - h) / mg) + 1, maxj = floor((ng i + h + mg - 1) / mg), clamped
+    int q_lo = -((hh + mg - 1) / mg), r_lo = q_lo * -mg - hh;    // floor(-h / mg), remainder in [0, mg)
+    int q_hi = (hh + mg - 1) / mg, r_hi = (hh + mg - 1) - q_hi * mg;
+    const int rel0 = lane * C;
+    int i = -lane;
+    const int periods = m + 31;
+#pragma unroll 1
+    for (int p = 0; p < periods; ++p) {
+        ++i;
+        const bool act = i >= 1 && i <= m;
+        int minj = prev_min, w = 0;
+        if (act) {
+            r_lo += ng;
+            if (r_lo >= mg) { r_lo -= mg; ++q_lo; }
+            r_hi += ng;
+            if (r_hi >= mg) { r_hi -= mg; ++q_hi; }
+            minj = min(max(q_lo + 1, 0), n);
+            w = max(min(q_hi, n + 1) - minj, 0);
+        }
+        const bool shifted = minj != prev_min;                    // s = 1
+        const int up_lim = prev_w - (shifted ? 1 : 0);            // the cell above rel exists iff rel < up_lim
+        const double di = (double)i;
+        double dj = (double)(minj + rel0);
+        const double *rp = rtab + (act ? i + minj + rel0 : 0);
+        double left = __shfl_up_sync(0xffffffffu, V[C - 1], 1);
+        if (lane == 0) left = 1.0;
+        double v0_next = 1.0;
+#pragma unroll
+        for (int q = 0; q < C; ++q) {
+            double up = shifted ? (q + 1 < C ? U[q + 1 < C ? q + 1 : q] : v0_next) : U[q];
+            up = (rel0 + q < up_lim) ? up : 1.0;
+            const double rden = __ldg(rp + q);
+            const double val = div_by_recip(NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(left, dj)), di + dj, rden);
+            V[q] = (rel0 + q < w) ? val : V[q];
+            left = V[q];
+            dj += 1.0;
+            if (q == 0) v0_next = __shfl_down_sync(0xffffffffu, V[0], 1);   // lane l + 1's strip starts here
+        }
+        if (act) {
+            if (i == m) {                                         // C(m, n)
+                const int reln = n - minj - rel0;
+#pragma unroll
+                for (int q = 0; q < C; ++q)
+                    if (q == reln && rel0 + q < w) *p_out_q = clip01(V[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < C; ++q) U[q] = V[q];
+            prev_min = minj;
+            prev_w = w;
+        }
+    }
+    __syncwarp();
+}
+
+// widest strip the strip form is compiled for (columns of band per lane)
+#define KS_STRIP_MAX 8
+__device__ __forceinline__ bool strip_dispatch(const double *__restrict__ rtab, int lane, const KsProblem &k,
+                                               double *p_out_q) {
+    // a row of the band has at most floor(2 h / mg) + 2 cells
+    const long long wmax = min(2 * k.h / k.mg + 2, (long long)k.n + 1);
+    if (wmax > 32 * KS_STRIP_MAX || k.m + k.n + 2 + 32 * KS_STRIP_MAX >= NCB_KS_RTAB_SIZE) return false;
+    const int c = (int)((wmax + 31) / 32);
+    switch (c) {
+        case 0: case 1: case 2: strip_problem<2>(rtab, lane, k, p_out_q); break;
+        case 3: strip_problem<3>(rtab, lane, k, p_out_q); break;
+        case 4: strip_problem<4>(rtab, lane, k, p_out_q); break;
+        case 5: strip_problem<5>(rtab, lane, k, p_out_q); break;
+        case 6: strip_problem<6>(rtab, lane, k, p_out_q); break;
+        default: strip_problem<8>(rtab, lane, k, p_out_q); break;
+    }
+    return true;
+}
+
 // ---- CTA per problem: lockstep wavefront over 2 x THREADS rows ------------------------------
 // The problems with the most band cells (a high-coverage position with a moderate shift: up to
 // 2 x 10^7 cells) would keep one warp busy for tens of milliseconds after everything else is
@@ -578,7 +677,11 @@ ks_wave_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p
             idx = __shfl_sync(0xffffffffu, idx, 0);
             if (idx >= hi) break;
             const int q = w.list[idx];
-            warp_problem<RING>(prev, w.rtab, lane, make_problem(n0[q], n1[q], h[q]), p_out + q);
+            const KsProblem k = make_problem(n0[q], n1[q], h[q]);
+#if KS_USE_STRIP
+            if (strip_dispatch(w.rtab, lane, k, p_out + q)) continue;
+#endif
+            warp_problem<RING>(prev, w.rtab, lane, k, p_out + q);
         }
     }
 }

@@ -73,7 +73,8 @@ enum { NCB_KS_KIND_SMALL = 0,  /* unequal sizes, DP window <= NCB_KS_SMALL_WINDO
 #define NCB_KS_RING_FULL (NCB_MAX_READS / 2 + 1)   /* the HUGE kind holds the whole row: no wrap */
 #define NCB_KS_NBINS (NCB_KS_KINDS * NCB_KS_BUCKETS)
 
-#define NCB_KS_RTAB_SIZE (NCB_MAX_READS + 64)   /* reciprocals of i + j <= n0 + n1 <= NCB_MAX_READS */
+#define NCB_KS_RTAB_SIZE (NCB_MAX_READS + 320)  /* reciprocals of i + j <= n0 + n1 <= NCB_MAX_READS; the strip form
+                                                   reads up to 256 entries past the last divisor it uses */
 
 struct NcbKsWork {
     const double *rtab; // [NCB_KS_RTAB_SIZE] correctly rounded reciprocals of the integers (per handle)

@@ -8,7 +8,7 @@ from nanocompore_b200 import _lib as L
 from nanocompore_b200.engine import Engine, pack_csr
 from nanocompore_b200.synthetic import make_transcript, BASE_SEED
 sets = {}
-for reads, npos in ((5000, 250), (5000, 2500), (1000, 400)):
+for reads, npos in ((5000, 250), (5000, 2500), (1000, 400), (1000, 5000), (400, 10000)):
     rng = np.random.default_rng(BASE_SEED + 5)
     txs = [make_transcript(rng, npos, reads) for _ in range(2)]
     batch = pack_csr([(t.data, t.samples, t.conditions) for t in txs])[0].to('cuda')
