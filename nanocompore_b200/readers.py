@@ -72,6 +72,36 @@ def encode_kmer(kmer):
     return code
 
 
+_CODE_TABLE = np.full(256, -1, dtype=np.int64)
+for _b, _c in _BASE_CODE.items():
+    _CODE_TABLE[ord(_b)] = _c
+
+
+def encode_kmers(seq, positions, klen):
+    """``encode_kmer(seq[p:p + klen])`` for every p of ``positions`` at once (the ``kmer`` column of
+    run.py:461-463 is a Python call per result row in the reference).  A k-mer cut short by the end of
+    the sequence is encoded over the bases it has, like the slice; a bad nucleotide raises the scalar
+    function's error."""
+    pos = np.asarray(positions, dtype=np.int64)
+    codes = _CODE_TABLE[np.frombuffer(seq.encode('latin-1'), dtype=np.uint8)]
+    out = np.zeros(pos.size, dtype=np.int64)
+    full = (pos >= 0) & (pos + klen <= codes.size)
+    p = pos[full]
+    acc = np.zeros(p.size, dtype=np.int64)
+    bad = np.zeros(p.size, dtype=bool)
+    for k in range(klen):
+        c = codes[p + k]
+        bad |= c < 0
+        acc = (acc << 2) | np.maximum(c, 0)
+    if bad.any():
+        q = int(p[np.nonzero(bad)[0][0]])
+        encode_kmer(seq[q:q + klen])                # raises with the reference's message
+    out[full] = acc
+    for i in np.nonzero(~full)[0]:
+        out[i] = encode_kmer(seq[pos[i]:pos[i] + klen])
+    return out
+
+
 def _threads():
     return min(16, os.cpu_count() or 1)
 
@@ -423,7 +453,7 @@ class TranscriptPipeline:
                                               res['counts'][:, :, sel][:, :, keep])
             seq = getattr(t, 'seq', None)
             if frame is not None and seq:
-                frame['kmer'] = [encode_kmer(seq[p:p + klen]) for p in frame.pos]   # run.py:461-463
+                frame['kmer'] = encode_kmers(seq, frame.pos.to_numpy(), klen)       # run.py:461-463
             out[i] = (t, frame)
         return out
 

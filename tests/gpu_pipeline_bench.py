@@ -1,0 +1,83 @@
+"""
+Files to result frames on one GPU: the whole of `Worker.run` (run.py:376-509) for a set of
+transcripts -- native readers (Uncalled4 BAM or SQLite blobs), read selection, rows -> pinned CSR,
+ncb_compare, frame assembly -- through readers.TranscriptPipeline.run_stream (read / pack of the next
+batch under the kernels of this one).  Supplementary to bench.py, which starts from packed batches.
+
+    python tests/gpu_pipeline_bench.py [--reads 400] [--positions 2000] [--transcripts 24] [--batch 8]
+
+Prints one JSON line per input format: tested positions/s from files, and where the time goes.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import bench_readers as BR  # noqa: E402
+from nanocompore_b200 import readers as R  # noqa: E402
+from nanocompore_b200.comparisons import TranscriptComparator  # noqa: E402
+from nanocompore_b200.config import PathConfig  # noqa: E402
+
+
+class Transcript:
+    def __init__(self, ref_id, name, seq):
+        self.id, self.name, self.seq, self.length = ref_id, name, seq, len(seq)
+
+
+class Worker:
+    def log(self, level, msg):
+        pass
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--reads', type=int, default=400, help='reads per transcript (all samples)')
+    ap.add_argument('--positions', type=int, default=2000)
+    ap.add_argument('--transcripts', type=int, default=24)
+    ap.add_argument('--batch', type=int, default=8)
+    args = ap.parse_args()
+    rng = np.random.default_rng(5)
+    with tempfile.TemporaryDirectory() as tmp:
+        refs, bams, dbs = BR.make_files(tmp, args.transcripts, args.positions, args.reads // 4)
+        seq = ''.join(rng.choice(list('ACGT'), args.positions))
+        transcripts = [Transcript(i + 1, name, seq) for i, (name, _) in enumerate(refs)]
+        for kind, paths in (('uncalled4_bam', bams), ('sqlite_db', dbs)):
+            key = 'bam' if kind == 'uncalled4_bam' else 'db'
+            cfg = PathConfig(dict(data={'kd': {'kd1': {key: paths['kd1']}, 'kd2': {key: paths['kd2']}},
+                                        'wt': {'wt1': {key: paths['wt1']}, 'wt2': {key: paths['wt2']}}},
+                                  depleted_condition='kd', kit='RNA002', comparison_methods=['GMM', 'KS'],
+                                  min_coverage=30))
+            reader = R.Uncalled4Reader(cfg) if kind == 'uncalled4_bam' else R.DbReader(cfg)
+            pipe = R.TranscriptPipeline(cfg, reader, TranscriptComparator(cfg, Worker()), 'cuda:0')
+            list(pipe.run_stream(transcripts[:2], batch_size=2))          # warm-up: context, buffers
+            t0 = time.perf_counter()
+            rows = 0
+            for _, df in pipe.run_stream(transcripts, batch_size=args.batch):
+                rows += 0 if df is None else len(df)
+            total = time.perf_counter() - t0
+            # the stages alone, for the breakdown
+            t0 = time.perf_counter()
+            prepared = pipe.prepare(transcripts[:args.batch])
+            t_prepare = (time.perf_counter() - t0) / args.batch
+            t0 = time.perf_counter()
+            pipe.finish(prepared)
+            t_finish = (time.perf_counter() - t0) / args.batch
+            print(json.dumps({
+                "format": kind, "transcripts": len(transcripts), "positions_per_transcript": args.positions,
+                "reads_per_transcript": args.reads, "host_cores": os.cpu_count(), "batch": args.batch,
+                "tested_positions": rows, "seconds": total, "tested_positions_per_s": rows / total,
+                "ms_per_transcript": {"read_select_pack": 1e3 * t_prepare, "compare_and_frames": 1e3 * t_finish}}),
+                flush=True)
+            reader.close()
+
+
+if __name__ == '__main__':
+    main()

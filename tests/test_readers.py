@@ -317,3 +317,16 @@ def test_encode_kmer():
     assert R.encode_kmer('AAAAA') == 0 and R.encode_kmer('ACGTT') == 0b0010011111
     with pytest.raises(RuntimeError):
         R.encode_kmer('ACGNN')
+
+
+def test_encode_kmers_is_the_scalar_function_per_row():
+    rng = np.random.default_rng(0)
+    seq = ''.join(rng.choice(list('ACGTacgt'), 300))
+    pos = np.array([0, 1, 5, 100, 294, 295, 296, 299, 298])       # the last k-mers are cut short by the end
+    for klen in (5, 9):
+        assert list(R.encode_kmers(seq, pos, klen)) == [R.encode_kmer(seq[p:p + klen]) for p in pos]
+    assert R.encode_kmers(seq, np.array([], dtype=np.int64), 5).size == 0
+    bad = seq[:50] + 'N' + seq[50:]
+    assert list(R.encode_kmers(bad, np.array([10, 60]), 5)) == [R.encode_kmer(bad[10:15]), R.encode_kmer(bad[60:65])]
+    with pytest.raises(RuntimeError, match="Bad nucleotide in kmer"):
+        R.encode_kmers(bad, np.array([10, 48]), 5)
