@@ -29,6 +29,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -58,12 +59,31 @@ inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
 
 }  // namespace
 
+// Message of the last failure on a handle.  Transcripts may be read from one handle by several
+// threads at once (the tables below are read-only after ncb_bam_open); only this text is written,
+// so its writers take a lock.
+struct ErrorText {
+    std::mutex mu;
+    std::string text;
+    ErrorText &operator=(const std::string &s) {
+        std::lock_guard<std::mutex> g(mu);
+        text = s;
+        return *this;
+    }
+    ErrorText &operator=(const char *s) { return *this = std::string(s); }
+    void clear() {
+        std::lock_guard<std::mutex> g(mu);
+        if (!text.empty()) text.clear();
+    }
+    const char *c_str() const { return text.c_str(); }
+};
+
 struct ncb_bam {
     std::string path;
     const uint8_t *map = nullptr;   // the whole file, read-only mapping
     int64_t file_size = 0;
     int threads = 1;
-    std::string error;
+    ErrorText error;
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_len;
     std::unordered_map<std::string, int32_t> ref_index;

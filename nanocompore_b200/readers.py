@@ -216,6 +216,9 @@ class NativeBam:
 class Uncalled4Reader:
     """``Uncalled4Worker.setup`` + ``_read_data`` (run.py:657-718)."""
 
+    # several transcripts may be read at once: the native handles are read-only after the index is built
+    concurrent_reads = True
+
     def __init__(self, config, threads=None):
         self._conf = config
         self._bams = {sample: NativeBam(bam, threads)
@@ -260,6 +263,8 @@ class Uncalled4Reader:
 class DbReader:
     """``GenericWorker.setup`` + ``_read_data`` (run.py:726-848) over the SQLite stores written by
     the reference's preprocessing (eventalign_collapse / Remora)."""
+
+    concurrent_reads = False      # one sqlite3 connection per sample: transcripts are read one after the other
 
     def __init__(self, config):
         self._conf = config
@@ -406,8 +411,16 @@ class TranscriptPipeline:
         native calls release the GIL, so this overlaps the kernels of the batch before)."""
         offset = self._conf.get_motor_dwell_offset()
         live, row_sets, masks = [], [], []
-        for i, t in enumerate(transcripts):
-            rows, keep = self.read(t)
+        # a transcript keeps one thread per sample busy: with more cores than samples several
+        # transcripts are decoded at once (the native calls release the GIL)
+        n_samples = max(len(self._conf.get_sample_ids()), 1)
+        workers = min(len(transcripts), max(_threads() // n_samples, 1))
+        if workers > 1 and getattr(self._reader, 'concurrent_reads', False):
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                results = list(ex.map(self.read, transcripts))
+        else:
+            results = [self.read(t) for t in transcripts]
+        for i, (rows, keep) in enumerate(results):
             if rows.n_reads == 0:
                 continue
             live.append(i)

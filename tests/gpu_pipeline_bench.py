@@ -70,11 +70,28 @@ def main():
             t0 = time.perf_counter()
             pipe.finish(prepared)
             t_finish = (time.perf_counter() - t0) / args.batch
+            # finer: the host stages of one batch, one after the other
+            tb = transcripts[:args.batch]
+            t0 = time.perf_counter()
+            raw = [reader.read(t.name, t.length) for t in tb]
+            t_read = (time.perf_counter() - t0) / args.batch
+            t0 = time.perf_counter()
+            sel = [R.select_reads(r, cfg.get_downsample_high_coverage(), cfg.get_min_coverage(), 0) for r in raw]
+            t_select = (time.perf_counter() - t0) / args.batch
+            t0 = time.perf_counter()
+            packed = R.pack_rows([r for r, _ in sel], 0, pin=True)
+            t_pack = (time.perf_counter() - t0) / args.batch
+            t0 = time.perf_counter()
+            res = pipe._comparator.compare_packed(packed[0], 'cuda:0', min_coverage=30)
+            t_compare = (time.perf_counter() - t0) / args.batch
+            stages = {"read": 1e3 * t_read, "select": 1e3 * t_select, "pack_pinned": 1e3 * t_pack,
+                      "compare_packed": 1e3 * t_compare, "frames": 1e3 * (t_finish - t_compare)}
             print(json.dumps({
                 "format": kind, "transcripts": len(transcripts), "positions_per_transcript": args.positions,
                 "reads_per_transcript": args.reads, "host_cores": os.cpu_count(), "batch": args.batch,
                 "tested_positions": rows, "seconds": total, "tested_positions_per_s": rows / total,
-                "ms_per_transcript": {"read_select_pack": 1e3 * t_prepare, "compare_and_frames": 1e3 * t_finish}}),
+                "ms_per_transcript": {"read_select_pack": 1e3 * t_prepare, "compare_and_frames": 1e3 * t_finish,
+                                      "stages": stages}}),
                 flush=True)
             reader.close()
 
