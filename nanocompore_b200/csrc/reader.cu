@@ -75,6 +75,7 @@ struct ErrorText {
         std::lock_guard<std::mutex> g(mu);
         if (!text.empty()) text.clear();
     }
+    bool empty() const { return text.empty(); }
     const char *c_str() const { return text.c_str(); }
 };
 
