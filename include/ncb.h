@@ -111,7 +111,10 @@ typedef struct {
     const int64_t *pos_offsets; /* CSR: [P+1]; dense: NULL                               */
     const float *signal;        /* CSR: [E][V] {intensity, dwell[, motor dwell]}; dense: [P][R][V] */
     const uint8_t *label;       /* CSR: [E]; dense: [R]                                  */
-    int32_t n_reads;            /* dense: R                                              */
+    int32_t n_reads;            /* dense: R.  CSR: an upper bound on the entries of a position if the
+                                   packer knows one (ncb_pack_* callers do), 0 = unknown.  The kernels of
+                                   the size classes above the bound are not launched; a position that
+                                   exceeds it gets NCB_POS_TOO_MANY_READS                                */
     int32_t n_vars;             /* V: 2, or 3 with the motor-dwell column of
                                    Worker._prepare_data (run.py:575-584); CSR: 0 means 2  */
 } ncb_batch;

@@ -252,6 +252,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     memset(&a, 0, sizeof(a));
     a.n_positions = P;
     a.n_reads = csr ? 0 : b->n_reads;
+    a.max_entries = b->n_reads > 0 ? b->n_reads : 0;
     a.n_vars = n_vars;
     a.tests = o.tests;
     a.n_samples = S;

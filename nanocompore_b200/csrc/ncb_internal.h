@@ -13,6 +13,7 @@ struct NcbDeviceArgs {
     int64_t n_positions;
     int32_t n_reads;             // dense R
     int32_t n_vars;              // floats per entry (2 for CSR, V for dense)
+    int32_t max_entries;         // upper bound on the entries of a position (dense: R), 0 = unknown
     // options
     int32_t tests;
     int32_t n_samples;

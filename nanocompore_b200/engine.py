@@ -53,6 +53,8 @@ class CsrBatch:
     pos_offsets: torch.Tensor
     signal: torch.Tensor
     label: torch.Tensor
+    max_entries: int = 0      # most entries a position has, if the packer knows (0 = unknown): the
+                              # size classes above it are not launched (ncb_batch.n_reads)
 
     @property
     def n_positions(self):
@@ -68,10 +70,11 @@ class CsrBatch:
     def to(self, device, non_blocking=False):
         return CsrBatch(self.pos_offsets.to(device, non_blocking=non_blocking),
                         self.signal.to(device, non_blocking=non_blocking),
-                        self.label.to(device, non_blocking=non_blocking))
+                        self.label.to(device, non_blocking=non_blocking), self.max_entries)
 
     def pin(self):
-        return CsrBatch(self.pos_offsets.pin_memory(), self.signal.pin_memory(), self.label.pin_memory())
+        return CsrBatch(self.pos_offsets.pin_memory(), self.signal.pin_memory(), self.label.pin_memory(),
+                        self.max_entries)
 
 
 def pack_csr(transcripts, pin=False, threads=None):
@@ -120,7 +123,7 @@ def pack_csr(transcripts, pin=False, threads=None):
         ptx.append(np.full(P, ti, dtype=np.int32))
         pidx.append(np.arange(P, dtype=np.int32))
         p0 += P
-    batch = CsrBatch(t_off, t_sig, t_lab)
+    batch = CsrBatch(t_off, t_sig, t_lab, int(all_counts.max()) if all_counts.size else 0)
     return (batch,
             np.concatenate(ptx) if ptx else np.zeros(0, np.int32),
             np.concatenate(pidx) if pidx else np.zeros(0, np.int32))
@@ -287,6 +290,7 @@ class Engine:
         b.signal = batch.signal.data_ptr()
         b.label = batch.label.data_ptr()
         b.n_vars = batch.signal.shape[1]     # 2, or 3 with the motor-dwell column
+        b.n_reads = min(int(batch.max_entries), 0x7fffffff)
         r = results.struct()
         s = self._stream(stream)
         self._check(self.lib.ncb_compare(self._handle, C.byref(b), C.byref(r), s))

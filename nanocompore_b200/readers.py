@@ -383,7 +383,7 @@ def pack_rows(row_sets, motor_dwell_offset=0, pin=False, threads=None):
         if row_sets else np.zeros(0, np.int32)
     pidx = np.concatenate([np.arange(r.n_positions, dtype=np.int32) for r in row_sets]) \
         if row_sets else np.zeros(0, np.int32)
-    return CsrBatch(t_off, t_sig, t_lab), ptx, pidx
+    return CsrBatch(t_off, t_sig, t_lab, int(all_counts.max()) if all_counts.size else 0), ptx, pidx
 
 
 class TranscriptPipeline:

@@ -103,3 +103,37 @@ def test_many_samples_and_unknown_sample_ids(engine_factory):
     eng4 = engine_factory(tests=('GMM',), min_coverage=0, n_samples=4)
     res4 = eng4.compare_dense(torch.from_numpy(data).cuda(), lab).numpy()
     assert (res4['counts'][:4] == res['counts'][:4]).all()
+
+
+def test_declared_max_entries_skips_classes_but_not_results(engine_factory):
+    """ncb_batch.n_reads of a CSR batch = the most entries a position has (the packers know it):
+    the size classes above it are not launched.  Same results as with an undeclared bound; a bound
+    that is too low is reported per position (NCB_POS_TOO_MANY_READS), never silently ignored."""
+    from nanocompore_b200.synthetic import make_transcript
+    eng = engine_factory(tests=('GMM', 'KS'), min_coverage=30, dwell_is_raw=True)
+    rng = np.random.default_rng(3)
+    txs = [make_transcript(rng, 200, 40), make_transcript(rng, 150, 150)]      # classes 0-1 and 2
+    batch, _, _ = pack_csr([(t.data, t.samples, t.conditions) for t in txs])
+    counts = np.diff(batch.pos_offsets.numpy())
+    assert batch.max_entries == counts.max() and 256 < batch.max_entries <= 512
+    dev = batch.to('cuda')
+    assert dev.max_entries == batch.max_entries
+    n0 = eng.kernel_launches()
+    want = eng.compare_csr(dev).numpy()
+    launched_declared = eng.kernel_launches() - n0
+    dev.max_entries = 0                                                        # undeclared: every class is launched
+    n0 = eng.kernel_launches()
+    got = eng.compare_csr(dev).numpy()
+    launched_all = eng.kernel_launches() - n0
+    assert launched_all - launched_declared == 2 * 4                           # four CTA classes x two phases
+    for key in ('status', 'pvalues', 'stats', 'counts'):
+        a, b = got[key].ravel(), want[key].ravel()
+        assert ((a == b) | (np.isnan(a.astype(np.float64)) & np.isnan(b.astype(np.float64)))).all(), key
+    dev.max_entries = 100                                                      # too low
+    res = eng.compare_csr(dev).numpy()
+    over = counts > 100
+    assert over.any() and ((res['status'][over] & L.NCB_POS_TOO_MANY_READS) != 0).all()
+    assert ((res['status'][~over] & L.NCB_POS_TOO_MANY_READS) == 0).all()
+    same = ~over
+    assert (res['pvalues'][L.PV['KS_INTENSITY']][same] == want['pvalues'][L.PV['KS_INTENSITY']][same]).all() or \
+        np.array_equal(np.isnan(res['pvalues'][L.PV['KS_INTENSITY']][same]), np.isnan(want['pvalues'][L.PV['KS_INTENSITY']][same]))
