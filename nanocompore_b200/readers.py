@@ -233,16 +233,25 @@ class Uncalled4Reader:
         with ThreadPoolExecutor(max_workers=max(len(self._bams), 1)) as ex:
             parts = list(ex.map(lambda kv: (kv[0],) + kv[1].read_uncalled4(transcript_name, ref_len, kit),
                                 self._bams.items()))
-        inten = np.concatenate([p[1] for p in parts]) if parts else np.empty((0, ref_len), np.float32)
-        dwell = np.concatenate([p[2] for p in parts]) if parts else np.empty((0, ref_len), np.float32)
         names = np.array([n for p in parts for n in p[3]], dtype=str)
         samples = np.array([sample_ids_of[p[0]] for p in parts for _ in p[3]], dtype=np.int64)
         conditions = np.array([cond_ids[cond_of[p[0]]] for p in parts for _ in p[3]], dtype=np.int64)
         # run.py:698-700: reads ordered by read id (the reference's argsort is not stable; equal
         # ids -- one read in two files -- keep the config order of their samples here)
         order = np.argsort(names, kind='stable')
-        rows = TranscriptRows(ref_len, inten[order], dwell[order], samples[order], conditions[order],
-                              names[order])
+        # the rows of every sample go straight to their place in that order: one copy of the signal
+        # (concatenating the samples and then reordering made two)
+        dest = np.empty_like(order)
+        dest[order] = np.arange(order.size)
+        inten = np.empty((order.size, ref_len), np.float32)
+        dwell = np.empty((order.size, ref_len), np.float32)
+        first = 0
+        for p in parts:
+            where = dest[first:first + len(p[3])]
+            inten[where] = p[1]
+            dwell[where] = p[2]
+            first += len(p[3])
+        rows = TranscriptRows(ref_len, inten, dwell, samples[order], conditions[order], names[order])
         # run.py:711-718
         valid = rows.invalid_ratios() < conf.get_max_invalid_kmers_freq()
         return rows if valid.all() else rows.take(valid)
