@@ -339,7 +339,7 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
 // column jlo - rho + t at step t, so b runs one column behind a and takes the cell above from
 // a's value of the step before -- the two cells of a step are independent of each other (two
 // chains to interleave), share the divisor i + j and its reciprocal, the loop, the exchange with
-// the neighbouring thread and the table / ring reads: 22 instead of 37 instructions per 32 cells.
+// the neighbouring thread and the table / ring reads: 24-26 instead of 37 instructions per 32 cells.
 struct WavePair {
     double di_a, di_b, dj_a, dj_b, den, a, b;   // a, b: the rows' latest cells (also their `left`)
     int j, jr, va, vb;      // a's column, a's column - jlo, band coordinates ng i - mg j + h - 1
