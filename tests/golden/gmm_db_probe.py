@@ -1,0 +1,129 @@
+"""
+How close is a restated mixture fit to the numbers gmm_gpu itself wrote into the reference's golden
+results database (tests/golden/golden_db.npz, see make_golden_db.py)?
+
+Runs the oracle pipeline on the fixture inputs (tests/golden/fixture_cfg1.npz) with several
+definitions of the 2-component fit -- the oracle's own (oracle/gmm.py) and scikit-learn's
+GaussianMixture under its four initialisations -- and prints, per definition, the agreement with
+the database on the BIC gate, the hard cluster counts, the chi-squared p-value and |LOR|.
+The fixture has 9-12 reads per position, so the fit is dominated by its initialisation: this is a
+characterisation of how far ANY restatement can be pinned by this database, not a pass/fail test.
+
+    python tests/golden/gmm_db_probe.py          # prints one JSON line per definition
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import prep as oprep                                   # noqa: E402
+from oracle.comparator import OracleComparator, OracleConfig       # noqa: E402
+from oracle.gmm import GMM                                         # noqa: E402
+
+
+def sklearn_gmm(init_params, seed=42):
+    from sklearn.mixture import GaussianMixture
+
+    class SkGMM:
+        def __init__(self, n_components, device='cpu', random_seed=None, dtype=None):
+            self.K = n_components
+            self.models = None
+
+        def fit(self, X):
+            X = np.asarray(X, dtype=np.float64)
+            self.models = []
+            for x in X:
+                v = x[~np.isnan(x).any(1)]
+                m = None
+                if len(v) >= max(2, self.K):
+                    try:
+                        with warnings.catch_warnings():
+                            warnings.simplefilter('ignore')
+                            m = GaussianMixture(self.K, covariance_type='full', tol=1e-3, reg_covar=1e-6,
+                                                max_iter=100, init_params=init_params,
+                                                random_state=seed).fit(v)
+                    except Exception:
+                        m = None
+                self.models.append(m)
+            return self
+
+        def bic(self, X):
+            X = np.asarray(X, dtype=np.float64)
+            out = np.full(len(X), np.nan)
+            for i, (x, m) in enumerate(zip(X, self.models)):
+                if m is not None:
+                    out[i] = m.bic(x[~np.isnan(x).any(1)])
+            return out
+
+        def predict_proba(self, X, force_cpu_result=False):
+            X = np.asarray(X, dtype=np.float64)
+            out = np.full(X.shape[:2] + (self.K,), np.nan)
+            for i, (x, m) in enumerate(zip(X, self.models)):
+                ok = ~np.isnan(x).any(1)
+                if m is not None:
+                    out[i, ok] = m.predict_proba(x[ok])
+            return out
+    return SkGMM
+
+
+def agreement(gmm_cls):
+    z = np.load(os.path.join(HERE, 'fixture_cfg1.npz'), allow_pickle=False)
+    g = np.load(os.path.join(HERE, 'golden_db.npz'), allow_pickle=False)
+    cols = [str(c) for c in g['columns']]
+    labels = [str(s) for s in z['sample_labels']]
+    sample_ids = dict(zip(labels, [int(i) for i in z['sample_ids']]))
+    db_tx = [str(t) for t in g['transcripts']]
+    tot = dict(common=0, same_reads=0, gate_same=0, both=0, counts_same=0, counts_swapped=0, p_same=0, lor_same=0,
+               db_tested=0, ours_tested=0)
+    for ti in range(int(z['n_transcripts'])):
+        db = g[f"tx{db_tx.index(str(z[f'tx{ti}/name']))}"]
+        data, samples, conditions, positions = oprep.prepare_data(
+            z[f'tx{ti}/raw'], z[f'tx{ti}/sample_ids'], z[f'tx{ti}/condition_ids'])
+        data, positions = oprep.filter_low_cov_positions(data, positions, conditions, 1)
+        cmp_ = OracleComparator(OracleConfig(comparison_methods=['GMM'], sample_ids=sample_ids,
+                                             depleted_condition_id=int(z['depleted_condition_id'])),
+                                gmm_cls=gmm_cls)
+        df = cmp_.compare_transcript(ti, data, samples, conditions, positions)
+        row = {int(p): i for i, p in enumerate(db[:, 0])}
+        keep = [i for i, p in enumerate(df['pos'].to_numpy()) if int(p) in row]
+        d = db[[row[int(df['pos'].to_numpy()[i])] for i in keep]]
+        col = lambda c: d[:, cols.index(c)]                          # noqa: E731
+        ours = np.stack([df[f'{s}_{k}'].to_numpy()[keep] for s in ('wt1', 'wt2', 'kd1', 'kd2')
+                         for k in ('mod', 'unmod')], 1)
+        theirs = np.stack([col(f'{s}_{k}') for s in ('WT1', 'WT2', 'KD1', 'KD2') for k in ('mod', 'unmod')], 1)
+        same_reads = (ours.reshape(-1, 4, 2).sum(2) == theirs.reshape(-1, 4, 2).sum(2)).all(1)
+        po, pt = df['GMM_chi2_pvalue'].to_numpy()[keep], col('GMM_chi2_pvalue')
+        lo, lt = df['GMM_LOR'].to_numpy()[keep].astype(np.float64), col('GMM_LOR')
+        to, tt = np.isfinite(po) & same_reads, np.isfinite(pt) & same_reads
+        both = to & tt
+        exact = (ours == theirs).all(1)
+        swapped = (ours.reshape(-1, 4, 2)[:, :, ::-1].reshape(-1, 8) == theirs).all(1)
+        tot['common'] += len(keep)
+        tot['same_reads'] += int(same_reads.sum())
+        tot['db_tested'] += int(tt.sum())
+        tot['ours_tested'] += int(to.sum())
+        tot['gate_same'] += int((to == tt)[same_reads].sum())
+        tot['both'] += int(both.sum())
+        tot['counts_same'] += int((exact & both).sum())
+        tot['counts_swapped'] += int((swapped & ~exact & both).sum())
+        tot['p_same'] += int(np.isclose(po[both], pt[both], rtol=1e-6).sum())
+        tot['lor_same'] += int(np.isclose(np.abs(lo[both]), np.abs(lt[both]), atol=2e-3).sum())
+    return tot
+
+
+if __name__ == '__main__':
+    defs = {'oracle/gmm.py (farthest pair + Lloyd)': GMM}
+    for ip in ('kmeans', 'k-means++', 'random_from_data', 'random'):
+        defs[f'sklearn GaussianMixture init_params={ip} random_state=42'] = sklearn_gmm(ip)
+    for name, cls in defs.items():
+        t = agreement(cls)
+        t['definition'] = name
+        t['gate_agreement'] = round(t['gate_same'] / t['same_reads'], 4)
+        t['partition_agreement_where_both_tested'] = round((t['counts_same'] + t['counts_swapped']) / t['both'], 4)
+        t['p_agreement_where_both_tested'] = round(t['p_same'] / t['both'], 4)
+        print(json.dumps(t), flush=True)

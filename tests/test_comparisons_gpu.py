@@ -88,6 +88,49 @@ def test_fixture_config1_rows_and_values():
     assert rows == 3519
 
 
+def test_fixture_config1_against_golden_db():
+    """The CUDA result frame against the numbers a real nanocompore run (real SciPy in float64, older
+    build: its condition 1 is today's condition 2) stored in the reference's golden results database
+    (tests/golden/golden_db.npz, see tests/test_oracle_golden_db.py for what it can pin): KS p-values
+    to 1e-9 and shift statistics to 2e-6 on >= 99 % of the 3437 rows (the rest predate a rule of the
+    current reader), per-sample read totals of the mixture fit on >= 99.5 %."""
+    z = load('fixture_cfg1.npz')
+    g = load('golden_db.npz')
+    cols = [str(c) for c in g['columns']]
+    db_tx = [str(t) for t in g['transcripts']]
+    n = ks_ok = shift_ok = reads_ok = 0
+    for ti in range(int(z['n_transcripts'])):
+        db = g[f"tx{db_tx.index(str(z[f'tx{ti}/name']))}"]
+        data, samples, conditions, positions = oprep.prepare_data(
+            z[f'tx{ti}/raw'], z[f'tx{ti}/sample_ids'], z[f'tx{ti}/condition_ids'])
+        data, positions = oprep.filter_low_cov_positions(data, positions, conditions, 1)
+        df = compare(config(), data, samples, conditions, positions)
+        pos = df['pos'].to_numpy()
+        row = {int(p): i for i, p in enumerate(db[:, 0])}
+        keep = np.array([i for i, p in enumerate(pos) if int(p) in row])
+        d = db[[row[int(pos[i])] for i in keep]]
+        col = lambda c: d[:, cols.index(c)]                          # noqa: E731
+        ks = np.ones(len(keep), dtype=bool)
+        for v in ('intensity', 'dwell'):
+            ks &= np.isclose(df[f'KS_{v}_pvalue'].to_numpy(dtype=np.float64)[keep], col(f'KS_{v}_pvalue'),
+                             rtol=1e-9, atol=0, equal_nan=True)
+        sh = np.ones(len(keep), dtype=bool)
+        for ours_c, theirs_c in ((1, 2), (2, 1)):
+            for s in ('mean', 'median', 'sd'):
+                for v in ('intensity', 'dwell'):
+                    sh &= np.isclose(df[f'c{ours_c}_{s}_{v}'].to_numpy(dtype=np.float64)[keep],
+                                     col(f'c{theirs_c}_{s}_{v}'), rtol=2e-6, atol=1e-6, equal_nan=True)
+        ours = np.stack([df[f'{s}_{k}'].to_numpy()[keep].astype(np.float64) for s in ('wt1', 'wt2', 'kd1', 'kd2')
+                         for k in ('mod', 'unmod')], 1)
+        theirs = np.stack([col(f'{s}_{k}') for s in ('WT1', 'WT2', 'KD1', 'KD2') for k in ('mod', 'unmod')], 1)
+        n += len(keep)
+        ks_ok += int(ks.sum())
+        shift_ok += int(sh.sum())
+        reads_ok += int((ours.reshape(-1, 4, 2).sum(2) == theirs.reshape(-1, 4, 2).sum(2)).all(1).sum())
+    assert n == 3437
+    assert ks_ok >= 0.99 * n and shift_ok >= 0.99 * n and reads_ok >= 0.995 * n, (ks_ok, shift_ok, reads_ok, n)
+
+
 @pytest.mark.parametrize('case', range(6))
 def test_synthetic_against_reference(case):
     """cases 4, 5: motor_dwell_offset > 0 -- 18 shift statistics, 2- and 3-variable mixtures."""

@@ -1,0 +1,82 @@
+"""
+The oracle against the reference's golden results database (tests/golden/golden_db.npz, extracted
+from /root/reference/tests/fixtures/out_sampComp_sql.db by tests/golden/make_golden_db.py): 3437 rows
+a real nanocompore run (older build, real SciPy 1.15 in float64, real gmm_gpu) wrote for the fixture
+BAMs.  CPU only.
+
+What the database can pin, and how hard:
+  * KS p-values (float64 in the database): the oracle's agree to 1e-9 relative on >= 99 % of the
+    common positions; the rest predate the "-32768 -> NaN" rule of the current reader
+    (uncalled4.py:103-107), as SURVEY 8c found with the unmodified reference.
+  * shift statistics: the database's condition 1 is today's condition 2 (labels WT*/KD*), float32
+    values stored as doubles: equal to 2e-6 relative on >= 99 % of the common positions.
+  * reads that enter the mixture fit: the per-sample totals of the cluster counts are equal on
+    >= 99.5 % of the positions (same outlier filter, same valid-read rule).
+  * the mixture fit itself: NOT pinned.  With 9-12 reads per position the fit is decided by its
+    initialisation: scikit-learn's own GaussianMixture under its four initialisations agrees with
+    the database on 65-72 % of the BIC gates and on 33-47 % of the hard partitions
+    (tests/golden/gmm_db_probe.py, profiles/r1_gmm_golden_db.jsonl); oracle/gmm.py sits inside that
+    spread (71 % / 40 %).  The test below only keeps it there.
+"""
+import os
+
+import numpy as np
+
+from oracle import prep as oprep
+from oracle.comparator import OracleComparator, OracleConfig
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+STAT = [f"{s}_{d}" for s in ('mean', 'median', 'sd') for d in ('intensity', 'dwell')]
+
+
+def test_oracle_against_golden_db():
+    z = np.load(os.path.join(GOLDEN, 'fixture_cfg1.npz'), allow_pickle=False)
+    g = np.load(os.path.join(GOLDEN, 'golden_db.npz'), allow_pickle=False)
+    assert int(g['total_rows']) == 3437
+    cols = [str(c) for c in g['columns']]
+    labels = [str(s) for s in z['sample_labels']]
+    sample_ids = dict(zip(labels, [int(i) for i in z['sample_ids']]))
+    db_tx = [str(t) for t in g['transcripts']]
+    n = ks_ok = shift_ok = reads_ok = gate_ok = 0
+    for ti in range(int(z['n_transcripts'])):
+        db = g[f"tx{db_tx.index(str(z[f'tx{ti}/name']))}"]
+        data, samples, conditions, positions = oprep.prepare_data(
+            z[f'tx{ti}/raw'], z[f'tx{ti}/sample_ids'], z[f'tx{ti}/condition_ids'])
+        data, positions = oprep.filter_low_cov_positions(data, positions, conditions, 1)
+        cmp_ = OracleComparator(OracleConfig(comparison_methods=['GMM', 'KS'], sample_ids=sample_ids,
+                                             depleted_condition_id=int(z['depleted_condition_id'])))
+        df = cmp_.compare_transcript(ti, data, samples, conditions, positions)
+        pos = df['pos'].to_numpy()
+        row = {int(p): i for i, p in enumerate(db[:, 0])}
+        keep = np.array([i for i, p in enumerate(pos) if int(p) in row])
+        # the database covers the positions the run tested; nearly all of ours are among them
+        assert len(keep) >= 0.95 * len(pos) and len(keep) >= 0.99 * len(db)
+        d = db[[row[int(pos[i])] for i in keep]]
+        col = lambda c: d[:, cols.index(c)]                          # noqa: E731
+        ks = np.ones(len(keep), dtype=bool)
+        for v in ('intensity', 'dwell'):
+            ks &= np.isclose(df[f'KS_{v}_pvalue'].to_numpy(dtype=np.float64)[keep], col(f'KS_{v}_pvalue'),
+                             rtol=1e-9, atol=0, equal_nan=True)
+        sh = np.ones(len(keep), dtype=bool)
+        for ours_c, theirs_c in ((1, 2), (2, 1)):
+            for s in STAT:
+                sh &= np.isclose(df[f'c{ours_c}_{s}'].to_numpy(dtype=np.float64)[keep], col(f'c{theirs_c}_{s}'),
+                                 rtol=2e-6, atol=1e-6, equal_nan=True)
+        ours = np.stack([df[f'{s}_{k}'].to_numpy()[keep] for s in ('wt1', 'wt2', 'kd1', 'kd2')
+                         for k in ('mod', 'unmod')], 1)
+        theirs = np.stack([col(f'{s}_{k}') for s in ('WT1', 'WT2', 'KD1', 'KD2') for k in ('mod', 'unmod')], 1)
+        same_reads = (ours.reshape(-1, 4, 2).sum(2) == theirs.reshape(-1, 4, 2).sum(2)).all(1)
+        gate = np.isfinite(df['GMM_chi2_pvalue'].to_numpy()[keep]) == np.isfinite(col('GMM_chi2_pvalue'))
+        n += len(keep)
+        ks_ok += int(ks.sum())
+        shift_ok += int(sh.sum())
+        reads_ok += int(same_reads.sum())
+        gate_ok += int((gate & same_reads).sum())
+    assert n == 3437
+    print(f"golden DB: KS {ks_ok / n:.4f}, shift {shift_ok / n:.4f}, reads {reads_ok / n:.4f}, "
+          f"BIC gate {gate_ok / reads_ok:.4f} of {n} rows")
+    assert ks_ok >= 0.99 * n
+    assert shift_ok >= 0.99 * n
+    assert reads_ok >= 0.995 * n
+    # soft: inside the spread scikit-learn's own initialisations show against this database
+    assert gate_ok >= 0.65 * reads_ok
