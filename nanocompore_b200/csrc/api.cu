@@ -120,6 +120,10 @@ static int check_opts(ncb_handle *h, const ncb_opts *o) {
     if (o->depleted_condition != 0 && o->depleted_condition != 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: depleted_condition must be 0 or 1");
     if (o->em_max_iter < 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: em_max_iter < 1");
     if (o->cluster_counts < NCB_COUNTS_NONE || o->cluster_counts > NCB_COUNTS_SOFT) return fail(h, NCB_ERR_INVALID, "ncb_opts: cluster_counts");
+    if (o->em_fp64 != 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: em_fp64 is reserved and must be 1");
+    if (!(o->em_tol >= 0.0) || !(o->reg_covar >= 0.0) || o->em_tol > 1e300 || o->reg_covar > 1e300)
+        return fail(h, NCB_ERR_INVALID, "ncb_opts: em_tol and reg_covar must be finite and >= 0");
+    if (o->min_coverage < 0) return fail(h, NCB_ERR_INVALID, "ncb_opts: min_coverage < 0");
     return NCB_OK;
 }
 
