@@ -2,7 +2,10 @@
 and through the oracle (a process pool on the host cores), every check of
 tests/test_gpu_parity.py:check_against_oracle per transcript.  Prints a JSON summary.
 
-    python tests/gpu_parity_sweep.py [n_transcripts] [positions] [processes]
+    python tests/gpu_parity_sweep.py [n_transcripts] [positions] [processes] [large]
+
+``large`` sweeps the CTA size classes (513-10 240 entries per position) and with them the wavefront
+forms of the exact-KS kernels: 300-5 000 reads per condition, ragged (3'-anchored read spans).
 """
 import json
 import os
@@ -17,6 +20,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 SHAPES = [(40, False), (100, False), (100, True), (150, False), (31, True), (230, False), (12, True)]
+SHAPES_LARGE = [(300, False), (505, True), (700, False), (1100, False), (2040, True), (2600, False), (4000, False),
+                (5000, False)]
 
 
 def gpu_results(jobs):
@@ -55,7 +60,9 @@ def main():
     n_tx = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     procs = int(sys.argv[3]) if len(sys.argv) > 3 else (os.cpu_count() or 1)
-    jobs = [(9000 + i, P) + SHAPES[i % len(SHAPES)] for i in range(n_tx)]
+    large = len(sys.argv) > 4 and sys.argv[4] == 'large'
+    shapes = SHAPES_LARGE if large else SHAPES
+    jobs = [((19000 if large else 9000) + i, P) + shapes[i % len(shapes)] for i in range(n_tx)]
     t0 = time.perf_counter()
     res = gpu_results(jobs)
     t_gpu = time.perf_counter() - t0
@@ -63,7 +70,7 @@ def main():
     with ProcessPoolExecutor(max_workers=procs) as ex:
         outcomes = list(ex.map(check, zip(jobs, res)))
     failures = [msg for _, _, msg in outcomes if msg]
-    print(json.dumps(dict(transcripts=n_tx, positions_checked=sum(k for _, k, _ in outcomes), failures=len(failures),
+    print(json.dumps(dict(transcripts=n_tx, reads_per_condition=sorted({n for n, _ in shapes}), positions_checked=sum(k for _, k, _ in outcomes), failures=len(failures),
                           first_failures=failures[:5], gpu_s=t_gpu, oracle_s=time.perf_counter() - t0)), flush=True)
     sys.exit(1 if failures else 0)
 
