@@ -20,8 +20,22 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 SHAPES = [(40, False), (100, False), (100, True), (150, False), (31, True), (230, False), (12, True)]
+SHAPES_MOTOR = [(40, 0.08), (120, 0.03), (31, 0.08), (230, 0.03), (100, 0.10), (60, 0.0), (300, 0.06), (700, 0.04)]
 SHAPES_LARGE = [(300, False), (505, True), (700, False), (1100, False), (2040, True), (2600, False), (4000, False),
                 (5000, False)]
+
+
+MOTOR = len(sys.argv) > 4 and sys.argv[4] == 'motor'
+
+
+def job_inputs(seed, P, n, q):
+    from nanocompore_b200.synthetic import make_transcript
+    from oracle import prep as oprep
+    if MOTOR:      # q is the gap rate
+        tx = make_transcript(np.random.default_rng(seed), P, n, gap_rate=q)
+        return oprep.prepare_data(tx.data, tx.samples, tx.conditions, 7)
+    tx = make_transcript(np.random.default_rng(seed), P, n, quantised=q)
+    return oprep.prepare_data(tx.data, tx.samples, tx.conditions)
 
 
 def gpu_results(jobs):
@@ -29,11 +43,10 @@ def gpu_results(jobs):
     from nanocompore_b200.engine import Engine, make_labels
     from oracle import prep as oprep
     from nanocompore_b200.synthetic import make_transcript
-    eng = Engine(0, tests=('KS', 'MW', 'TT', 'GMM'), with_logit=True)
+    eng = Engine(0, tests=('KS', 'MW', 'TT', 'GMM'), with_logit=not MOTOR, **(dict(min_coverage=0) if MOTOR else {}))
     out = []
     for seed, P, n, q in jobs:
-        tx = make_transcript(np.random.default_rng(seed), P, n, quantised=q)
-        data, samples, conditions, _ = oprep.prepare_data(tx.data, tx.samples, tx.conditions)
+        data, samples, conditions, _ = job_inputs(seed, P, n, q)
         res = eng.compare_dense(torch.from_numpy(data).cuda(), torch.from_numpy(make_labels(samples, conditions)).cuda(),
                                 diagnostics=True).numpy()
         out.append(res)
@@ -45,15 +58,15 @@ def check(args):
     (seed, P, n, q), res = args
     os.environ['CUDA_VISIBLE_DEVICES'] = ''
     import test_gpu_parity as T
-    from nanocompore_b200.synthetic import make_transcript
-    from oracle import prep as oprep
-    tx = make_transcript(np.random.default_rng(seed), P, n, quantised=q)
-    data, samples, conditions, _ = oprep.prepare_data(tx.data, tx.samples, tx.conditions)
+    data, samples, conditions, positions = job_inputs(seed, P, n, q)
     try:
-        ok = T.check_against_oracle(res, data, samples, conditions)
+        if MOTOR:
+            ok, _ = T.check_three_variables(res, data, samples, conditions, positions)
+        else:
+            ok = T.check_against_oracle(res, data, samples, conditions)
         return seed, int(ok.sum()), None
     except AssertionError as e:
-        return seed, 0, f"seed {seed} n {n} quantised {q}: {str(e)[:400]}"
+        return seed, 0, f"seed {seed} n {n} {'gap rate' if MOTOR else 'quantised'} {q}: {str(e)[:400]}"
 
 
 def main():
@@ -61,8 +74,8 @@ def main():
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     procs = int(sys.argv[3]) if len(sys.argv) > 3 else (os.cpu_count() or 1)
     large = len(sys.argv) > 4 and sys.argv[4] == 'large'
-    shapes = SHAPES_LARGE if large else SHAPES
-    jobs = [((19000 if large else 9000) + i, P) + shapes[i % len(shapes)] for i in range(n_tx)]
+    shapes = SHAPES_LARGE if large else SHAPES_MOTOR if MOTOR else SHAPES
+    jobs = [((19000 if large else 29000 if MOTOR else 9000) + i, P) + shapes[i % len(shapes)] for i in range(n_tx)]
     t0 = time.perf_counter()
     res = gpu_results(jobs)
     t_gpu = time.perf_counter() - t0

@@ -297,24 +297,17 @@ def test_bh_fdr_unit(engine_factory):
     assert_equal_nan(qd, got, 'device vs host staging')
 
 
-@pytest.mark.parametrize('n,gap', [(40, 0.08), (120, 0.03)])
-def test_motor_dwell_three_variables(engine_factory, n, gap):
-    """motor_dwell_offset > 0: 18 shift statistics, outlier rule over 3 variables, and the split into
-    3-variable / 2-variable mixtures by the 90 % rule (comparisons.py:285-335, 395-403)."""
+def check_three_variables(res, data, samples, conditions, positions, motor_dwell_offset=7):
+    """Every check of the 3-variable path against the oracle; returns (kept positions, fitted in 3 variables)."""
     from oracle.comparator import OracleComparator, OracleConfig
-    eng = engine_factory(tests=ALL_TESTS, with_logit=False, min_coverage=0)
-    rng = np.random.default_rng(77 + n)
-    tx = make_transcript(rng, 90, n, gap_rate=gap)
-    data, samples, conditions, positions = oprep.prepare_data(tx.data, tx.samples, tx.conditions, 7)
-    assert data.shape[2] == 3
-    res = run_dense(eng, data, samples, conditions)
-    cmp_ = OracleComparator(OracleConfig(comparison_methods=list(ALL_TESTS), motor_dwell_offset=7))
+    cmp_ = OracleComparator(OracleConfig(comparison_methods=list(ALL_TESTS), motor_dwell_offset=motor_dwell_offset))
     df = cmp_.compare_transcript(0, data, samples, conditions, positions)
     shift = ostats.shift_stats(data, conditions)
     std_data, outliers, bad, _ = ostats.outlier_standardise(data)
     assert_equal_nan((res['status'] & L.NCB_POS_BAD_STD) != 0, bad, 'bad-std pattern (3 variables)')
     ok = ~bad
-    assert ok.sum() == len(df) and bad.sum() >= 7          # the last 7 positions have no motor dwell
+    # the last `motor_dwell_offset` positions have no motor dwell
+    assert ok.sum() == len(df) and bad.sum() >= motor_dwell_offset
     for c in (1, 2):
         for st in ('mean', 'median', 'sd'):
             for dim, key in (('intensity', 'INTENSITY'), ('dwell', 'DWELL'), ('motor_dwell', 'MOTOR')):
@@ -325,10 +318,8 @@ def test_motor_dwell_three_variables(engine_factory, n, gap):
         for v in ('intensity', 'dwell'):
             assert_pvalues_close(res['pvalues'][L.PV[f'{t}_{v.upper()}']][ok], df[f'{t}_{v}_pvalue'].to_numpy(),
                                  f'{t} {v} p')
-    # both kinds of position occur
     valid = ~np.isnan(std_data[ok])
     use3 = (valid[:, :, 0] & valid[:, :, 2]).sum(1) >= 0.9 * valid[:, :, 0].sum(1)
-    assert use3.any() and ((~use3).any() or gap < 0.05)    # the gappy case has both kinds
     assert_pvalues_close(res['pvalues'][L.PV['GMM_CHI2']][ok], df['GMM_chi2_pvalue'].to_numpy(), 'GMM chi2 p')
     assert_equal_nan(res['stats'][L.ST['GMM_LOR']][ok], df['GMM_LOR'].to_numpy(dtype=np.float32), 'LOR')
     for label, sid in SAMPLE_IDS.items():
@@ -338,6 +329,22 @@ def test_motor_dwell_three_variables(engine_factory, n, gap):
     n_fit = np.where(use3, valid.all(2).sum(1), (valid[:, :, 0] & valid[:, :, 1]).sum(1))
     cont = sum(res['diag_i64'][L.DI[f'CONT_{c}{k}']] for c in (0, 1) for k in (0, 1))[ok]
     assert_equal_nan(cont, n_fit, 'reads in the fit')
+    return ok, use3
+
+
+@pytest.mark.parametrize('n,gap', [(40, 0.08), (120, 0.03)])
+def test_motor_dwell_three_variables(engine_factory, n, gap):
+    """motor_dwell_offset > 0: 18 shift statistics, outlier rule over 3 variables, and the split into
+    3-variable / 2-variable mixtures by the 90 % rule (comparisons.py:285-335, 395-403)."""
+    eng = engine_factory(tests=ALL_TESTS, with_logit=False, min_coverage=0)
+    rng = np.random.default_rng(77 + n)
+    tx = make_transcript(rng, 90, n, gap_rate=gap)
+    data, samples, conditions, positions = oprep.prepare_data(tx.data, tx.samples, tx.conditions, 7)
+    assert data.shape[2] == 3
+    res = run_dense(eng, data, samples, conditions)
+    _, use3 = check_three_variables(res, data, samples, conditions, positions)
+    # both kinds of position occur
+    assert use3.any() and ((~use3).any() or gap < 0.05)    # the gappy case has both kinds
 
 
 def test_correct_pvalues_mirror(engine_factory):
