@@ -21,11 +21,14 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 SHAPES = [(40, False), (100, False), (100, True), (150, False), (31, True), (230, False), (12, True)]
 SHAPES_MOTOR = [(40, 0.08), (120, 0.03), (31, 0.08), (230, 0.03), (100, 0.10), (60, 0.0), (300, 0.06), (700, 0.04)]
+SHAPES_CSR = [(40, False), (100, True), (150, False), (230, False), (505, True), (1100, False), (12, True),
+              (2600, False)]
 SHAPES_LARGE = [(300, False), (505, True), (700, False), (1100, False), (2040, True), (2600, False), (4000, False),
                 (5000, False)]
 
 
 MOTOR = len(sys.argv) > 4 and sys.argv[4] == 'motor'
+CSR = len(sys.argv) > 4 and sys.argv[4] == 'csr'
 
 
 def job_inputs(seed, P, n, q):
@@ -45,6 +48,17 @@ def gpu_results(jobs):
     from nanocompore_b200.synthetic import make_transcript
     eng = Engine(0, tests=('KS', 'MW', 'TT', 'GMM'), with_logit=not MOTOR, **(dict(min_coverage=0) if MOTOR else {}))
     out = []
+    if CSR:
+        from nanocompore_b200.engine import pack_csr
+        for b in range(0, len(jobs), 8):
+            txs = [job_inputs(*j)[:3] for j in jobs[b:b + 8]]
+            batch, ptx, _ = pack_csr(txs, pin=True)
+            host = eng.compare_csr(batch, diagnostics=True).numpy()
+            for ti in range(len(txs)):
+                sel = ptx == ti
+                out.append({k: (np.ascontiguousarray(v[..., sel]) if v is not None else None) for k, v in host.items()})
+        eng.close()
+        return out
     for seed, P, n, q in jobs:
         data, samples, conditions, _ = job_inputs(seed, P, n, q)
         res = eng.compare_dense(torch.from_numpy(data).cuda(), torch.from_numpy(make_labels(samples, conditions)).cuda(),
@@ -74,8 +88,8 @@ def main():
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     procs = int(sys.argv[3]) if len(sys.argv) > 3 else (os.cpu_count() or 1)
     large = len(sys.argv) > 4 and sys.argv[4] == 'large'
-    shapes = SHAPES_LARGE if large else SHAPES_MOTOR if MOTOR else SHAPES
-    jobs = [((19000 if large else 29000 if MOTOR else 9000) + i, P) + shapes[i % len(shapes)] for i in range(n_tx)]
+    shapes = SHAPES_LARGE if large else SHAPES_MOTOR if MOTOR else SHAPES_CSR if CSR else SHAPES
+    jobs = [((19000 if large else 29000 if MOTOR else 39000 if CSR else 9000) + i, P) + shapes[i % len(shapes)] for i in range(n_tx)]
     t0 = time.perf_counter()
     res = gpu_results(jobs)
     t_gpu = time.perf_counter() - t0
