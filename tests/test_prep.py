@@ -70,3 +70,40 @@ def test_downsample_keeps_the_most_complete_reads_per_condition():
     assert np.array_equal(out.numpy(), od, equal_nan=True) and (oc == c.numpy()).all()
     same, s2, c2 = prep.downsample(data, samples, cond, 12)
     assert same is data
+
+
+def test_reference_own_known_answers():
+    """The literal inputs of the reference's tests/test_run.py:70-193 (test_prepare_data_no_motor,
+    test_prepare_data_with_motor, test_downsample) and what the UNMODIFIED reference returned for
+    them, recorded by tests/golden/make_golden_prep.py while those tests passed."""
+    z = load('prep_ref.npz')
+    assert [str(t) for t in z['tests']] == ['test_prepare_data_no_motor', 'test_prepare_data_with_motor',
+                                            'test_downsample']
+    seen = []
+    for i in range(int(z['n_calls'])):
+        fn = str(z[f'call{i}/function'])
+        motor = int(z[f'call{i}/motor_dwell_offset'])
+        want = [z[f'call{i}/out{j}'] for j in range(4 if fn == '_prepare_data' else 3)]
+        if fn == '_prepare_data':
+            args = [z[f'call{i}/in{j}'] for j in range(3)]
+            got = prep.prepare_data(args[0].copy(), args[1], args[2], motor)
+            ora = oprep.prepare_data(args[0].copy(), args[1], args[2], motor)
+        else:
+            args = [z[f'call{i}/in{j}'] for j in range(3)]
+            max_reads = int(z[f'call{i}/in3'])
+            got = prep.downsample(torch.from_numpy(args[0]), torch.from_numpy(args[1]), torch.from_numpy(args[2]),
+                                  max_reads)
+            ora = oprep.downsample(args[0], args[1], args[2], max_reads)
+        assert len(got) == len(want) == len(ora)
+        for g, o, w in zip(got, ora, want):
+            g = g.numpy() if isinstance(g, torch.Tensor) else np.asarray(g)
+            assert g.shape == w.shape and np.asarray(o).shape == w.shape, fn
+            if w.dtype.kind == 'f':
+                # log10 in float32: libm (reference) vs correctly rounded (here), <= 2 ulps
+                np.testing.assert_allclose(g, w, rtol=3e-7, atol=1e-7, equal_nan=True, err_msg=fn)
+                np.testing.assert_allclose(np.asarray(o), w, rtol=3e-7, atol=1e-7, equal_nan=True, err_msg=fn)
+            else:
+                np.testing.assert_array_equal(g, w, err_msg=fn)
+                np.testing.assert_array_equal(np.asarray(o), w, err_msg=fn)
+        seen.append((fn, motor))
+    assert seen == [('_prepare_data', 0), ('_prepare_data', 2), ('_downsample', 0)]
