@@ -80,3 +80,34 @@ def test_oracle_against_golden_db():
     assert reads_ok >= 0.995 * n
     # soft: inside the spread scikit-learn's own initialisations show against this database
     assert gate_ok >= 0.65 * reads_ok
+
+
+def test_post_fit_columns_from_the_databases_own_counts():
+    """What follows the fit, pinned on gmm_gpu's own partitions: from the per-sample cluster counts the
+    database stores, the oracle's chi-squared test (Yates, +1 table: comparisons.py:380-392) gives the
+    database's GMM_chi2_pvalue to 1e-9 and |GMM_LOR| to its 3 decimals on all 1241 tested rows, and the
+    rule that names the modified cluster (lower frequency in the depleted condition, comparisons.py:
+    564-605) picks the database's `mod` column on every row -- with the other condition as the depleted
+    one it would on 79 % only."""
+    from oracle.gmm_test import calculate_lors, chi2_2x2_p, mod_cluster
+    g = np.load(os.path.join(GOLDEN, 'golden_db.npz'), allow_pickle=False)
+    cols = [str(c) for c in g['columns']]
+    tested = 0
+    for tx in ('tx0', 'tx1'):
+        d = g[tx]
+        col = lambda c: d[:, cols.index(c)]                          # noqa: E731
+        kd = np.stack([col('KD1_mod') + col('KD2_mod'), col('KD1_unmod') + col('KD2_unmod')], 1)
+        wt = np.stack([col('WT1_mod') + col('WT2_mod'), col('WT1_unmod') + col('WT2_unmod')], 1)
+        cont = np.stack([kd, wt], 1).astype(np.float32)      # (P, condition [kd, wt], cluster [mod, unmod])
+        p, lor = col('GMM_chi2_pvalue'), col('GMM_LOR')
+        t = np.isfinite(p)
+        assert (np.isfinite(lor) == t).all()
+        tested += int(t.sum())
+        got_p = np.array([chi2_2x2_p(c) for c in cont[t] + 1])
+        np.testing.assert_allclose(got_p, p[t], rtol=1e-9)
+        got_lor = calculate_lors(cont[t] + 1).astype(np.float64)
+        # the database does not say which cluster index was `mod`: the sign of the LOR is not recoverable
+        np.testing.assert_allclose(np.abs(got_lor), np.abs(lor[t]), atol=1e-6)
+        assert (mod_cluster(cont, 0) == 0).all()                 # depleted condition = kd
+        assert (mod_cluster(cont, 1)[t] == 0).mean() < 0.9       # the check discriminates
+    assert tested == 1241
