@@ -191,3 +191,23 @@ def test_igamc_against_scipy(hc):
     assert hc.hc_igamc(3.0, 0.0) == 1.0
     assert hc.hc_igamc(3.0, float('inf')) == 0.0
     assert np.isnan(hc.hc_igamc(3.0, float('nan')))
+
+
+def test_chi2_matches_the_reference_golden_results_database(hc):
+    """The kernel's chi-squared routine (ncb_math.cuh: chi2_2x2_p, called by gmm_tail on the +1 table)
+    on the contingency tables behind the 1241 tested rows of the reference's golden results database
+    (tests/golden/golden_db.npz: a real run, real SciPy): its GMM_chi2_pvalue to 1e-9."""
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_db.npz'), allow_pickle=False)
+    cols = [str(c) for c in g['columns']]
+    n = 0
+    for tx in ('tx0', 'tx1'):
+        d = g[tx]
+        col = lambda c: d[:, cols.index(c)]                          # noqa: E731
+        kd = (col('KD1_mod') + col('KD2_mod'), col('KD1_unmod') + col('KD2_unmod'))
+        wt = (col('WT1_mod') + col('WT2_mod'), col('WT1_unmod') + col('WT2_unmod'))
+        p = col('GMM_chi2_pvalue')
+        for i in np.nonzero(np.isfinite(p))[0]:
+            got = hc.hc_chi2_2x2_p(kd[0][i] + 1, kd[1][i] + 1, wt[0][i] + 1, wt[1][i] + 1)
+            assert abs(got - p[i]) <= 1e-9 * p[i], (i, got, p[i])
+            n += 1
+    assert n == 1241
