@@ -211,3 +211,40 @@ def test_chi2_matches_the_reference_golden_results_database(hc):
             assert abs(got - p[i]) <= 1e-9 * p[i], (i, got, p[i])
             n += 1
     assert n == 1241
+
+
+def test_ks_equal_sizes_match_the_reference_golden_results_database(hc):
+    """The kernels' equal-size exact-KS routine (ks_equal_p, the form ks_equal_kernel evaluates) on the
+    fixture positions with as many reads in one condition as in the other, against the float64
+    KS p-values a real run (real SciPy) stored in the reference's golden results database."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from oracle import prep as oprep, stats as ostats
+    from parity_utils import oracle_rank_stats
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'fixture_cfg1.npz'), allow_pickle=False)
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_db.npz'), allow_pickle=False)
+    cols = [str(c) for c in g['columns']]
+    db_tx = [str(t) for t in g['transcripts']]
+    n = ok = 0
+    for ti in range(int(z['n_transcripts'])):
+        db = g[f"tx{db_tx.index(str(z[f'tx{ti}/name']))}"]
+        data, samples, conditions, positions = oprep.prepare_data(
+            z[f'tx{ti}/raw'], z[f'tx{ti}/sample_ids'], z[f'tx{ti}/condition_ids'])
+        data, positions = oprep.filter_low_cov_positions(data, positions, conditions, 1)
+        std, _, bad, _ = ostats.outlier_standardise(data)
+        std, positions = std[~bad], positions[~bad]
+        rs = oracle_rank_stats(std, conditions)
+        row = {int(p): i for i, p in enumerate(db[:, 0])}
+        for i, p in enumerate(positions):
+            if int(p) not in row:
+                continue
+            for v, name in enumerate(('KS_intensity_pvalue', 'KS_dwell_pvalue')):
+                n0, n1, h = int(rs['n0'][i, v]), int(rs['n1'][i, v]), int(rs['ks_h'][i, v])
+                if n0 != n1 or n0 == 0:
+                    continue
+                want = db[row[int(p)], cols.index(name)]
+                got = min(1.0, max(0.0, hc.hc_ks_equal_p(n0, h)))
+                n += 1
+                ok += abs(got - want) <= 1e-9 * want
+    # the few misses are the rows where the database predates a rule of the current reader
+    assert n > 1000 and ok >= 0.99 * n, (ok, n)
