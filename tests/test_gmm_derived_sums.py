@@ -4,8 +4,8 @@ only ONE component's sufficient statistics are accumulated (the one with the sma
 before; 2-means cluster 0 in the Lloyd iterations), the other's are the totals of the position minus
 the first's.  The model below runs the kernel's formulation of the fit in numpy fp64 -- raw-moment
 M-step, responsibilities as 1 / (1 + e^-|d|) and its complement, log-likelihood as max + log(1 + e),
-derived sums -- and must agree with the oracle's definition (oracle/gmm.py: centred moments, softmax
-responsibilities, every sum taken directly) on the number of Lloyd and EM iterations, the hard
+derived sums, optionally the folded products of the A/B macro NCB_ACC_FOLD -- and must agree with
+the oracle's definition (oracle/gmm.py: centred moments, softmax responsibilities, every sum taken directly) on the number of Lloyd and EM iterations, the hard
 assignment of every read and the BIC, on ordinary, tiny-coverage, quantised and lopsided positions.
 It pins the numerics of the formulation (cancellation in the derived sums), not the kernel's bits:
 those are the GPU parity tests' and sweeps' job.
@@ -16,7 +16,7 @@ import pytest
 from oracle.gmm import GMM, EPS10, LOG_2PI
 
 
-def kernel_form_fit(X, derive=True, reg=1e-6, tol=1e-3, max_iter=100, kmeans_max_iter=20):
+def kernel_form_fit(X, derive=True, fold=False, reg=1e-6, tol=1e-3, max_iter=100, kmeans_max_iter=20):
     """X: (B, N, 2) with NaN rows.  Returns dict(n_kmeans, n_iter, pred (B,N) int8 with -1 on
     missing reads, loglik (B,))."""
     X = np.asarray(X, dtype=np.float64)
@@ -92,12 +92,18 @@ def kernel_form_fit(X, derive=True, reg=1e-6, tol=1e-3, max_iter=100, kmeans_max
         ll = ((np.maximum(l0, l1) + np.log1p(ex)) * vf).sum(1)
         return r0 * vf, r1 * vf, ll, d
 
+    def weighted(r):
+        if not fold:
+            return (feats * r[:, :, None]).sum(1)
+        rx, ry = r * x, r * y          # NCB_ACC_FOLD: second moments as (r x) x
+        return np.stack([r, rx, ry, rx * x, rx * y, ry * y], 2).sum(1)
+
     def stats(r0, r1, second):
         """sufficient statistics of both components; `second` (B,) bool: the component summed."""
         if not derive:
-            return (feats * r0[:, :, None]).sum(1), (feats * r1[:, :, None]).sum(1)
+            return weighted(r0), weighted(r1)
         rs = np.where(second[:, None], r1, r0)
-        small = (feats * rs[:, :, None]).sum(1)
+        small = weighted(rs)
         rest = T - small
         rest[:, 0] = np.maximum(rest[:, 0], 0.0)
         sec = second[:, None]
@@ -164,8 +170,8 @@ def test_derived_sums_agree_with_the_definition(kind, B, N):
     ref = GMM(2).fit(X)
     want_pred = np.where(~np.isnan(X).any(2), ref.predict_proba(X).argmax(2), -1)
     want_ll, _ = ref.loglik(X)
-    for derive in (False, True):
-        got = kernel_form_fit(X, derive=derive)
+    for derive, fold in ((False, False), (True, False), (True, True)):
+        got = kernel_form_fit(X, derive=derive, fold=fold)
         np.testing.assert_array_equal(got['n_kmeans'], ref.n_kmeans, err_msg=f'{kind} Lloyd iterations, derive={derive}')
         np.testing.assert_array_equal(got['n_iter'], ref.n_iter, err_msg=f'{kind} EM iterations, derive={derive}')
         np.testing.assert_array_equal(got['pred'], want_pred, err_msg=f'{kind} hard assignment, derive={derive}')
