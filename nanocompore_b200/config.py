@@ -89,15 +89,18 @@ class PathConfig:
     def get_max_invalid_kmers_freq(self):
         return self._config.get('max_invalid_kmers_freq', DEFAULT_MAX_INVALID_KMERS_FREQ)
 
-    def get_sample_condition_bam_data(self):
-        return [(sample, condition, samp_def['bam'])
-                for condition, samples in self.get_data().items()
-                for sample, samp_def in samples.items()]
+    def _sample_files(self, key):
+        """(sample, condition, path) triples in the order of the ``data`` section."""
+        out = []
+        for condition, replicates in self.get_data().items():
+            out.extend((sample, condition, entry[key]) for sample, entry in replicates.items())
+        return out
+
+    def get_sample_condition_bam_data(self):       # config.py: same name, same order
+        return self._sample_files('bam')
 
     def get_sample_condition_db_data(self):
-        return [(sample, condition, samp_def['db'])
-                for condition, samples in self.get_data().items()
-                for sample, samp_def in samples.items()]
+        return self._sample_files('db')
 
     def is_multi_replicate(self):
         return all(len(reps) > 1 for reps in self.get_data().values())
