@@ -2,6 +2,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 #include "ncb_internal.h"
@@ -130,7 +132,8 @@ static int check_opts(ncb_handle *h, const ncb_opts *o) {
 int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
     if (!out) return NCB_ERR_INVALID;
     *out = nullptr;
-    ncb_handle *h = new ncb_handle();
+    ncb_handle *h = new (std::nothrow) ncb_handle();
+    if (!h) return NCB_ERR_NOMEM;
     ncb_opts def;
     ncb_default_opts(&def);
     h->opts = opts ? *opts : def;
@@ -273,7 +276,12 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
         for (int i = 0; i < 5; ++i) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
-            h->ev_log.push_back(e);
+            try {   // nothing is thrown across the C ABI
+                h->ev_log.push_back(e);
+            } catch (const std::exception &) {
+                cudaEventDestroy(e);
+                return fail(h, NCB_ERR_NOMEM, "ncb_compare: timing log");
+            }
             h->ev[i] = e;
         }
         CK(cudaEventRecord(h->ev[0], s));
@@ -498,8 +506,14 @@ int ncb_context_combine(ncb_handle *h, int64_t n_tx, const int64_t *tx_offsets, 
     if (tx_offsets[0] != 0 || n < 0) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: bad tx_offsets");
     if (n > 0 && (!pos || !pvalues || !combined)) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: null pointer");
     // the dense track of a transcript spans its first to its last position (comparisons.py:445-459)
-    std::vector<int64_t> track(n_tx + 1, 0);
-    std::vector<int32_t> idx((size_t)n);
+    std::vector<int64_t> track;
+    std::vector<int32_t> idx;
+    try {   // nothing is thrown across the C ABI
+        track.assign((size_t)n_tx + 1, 0);
+        idx.resize((size_t)n);
+    } catch (const std::exception &) {
+        return fail(h, NCB_ERR_NOMEM, "ncb_context_combine: host staging");
+    }
     for (int64_t t = 0; t < n_tx; ++t) {
         const int64_t r0 = tx_offsets[t], r1 = tx_offsets[t + 1];
         if (r1 < r0 || r1 > n) return fail(h, NCB_ERR_INVALID, "ncb_context_combine: bad tx_offsets");

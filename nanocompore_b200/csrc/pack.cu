@@ -6,6 +6,7 @@
 // the dense tensor altogether.
 #include <math.h>
 #include <string.h>
+#include <exception>
 #include <thread>
 #include <vector>
 #include "ncb.h"
@@ -24,7 +25,11 @@ void parallel_for(int64_t n, int threads, F f) {
     for (int t = 0; t < threads; ++t) {
         const int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
         if (lo >= hi) break;
-        pool.emplace_back([=] { f(lo, hi); });
+        try {
+            pool.emplace_back([=] { f(lo, hi); });
+        } catch (const std::exception &) {
+            f(lo, hi);   // no thread (or no memory for one) to be had: the chunk runs here
+        }
     }
     for (auto &th : pool) th.join();
 }

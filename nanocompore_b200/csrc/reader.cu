@@ -29,6 +29,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <exception>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -38,6 +39,9 @@
 #include "ncb.h"
 
 namespace {
+
+// largest record accepted (a record holds one read: name, CIGAR, sequence, qualities and the signal tags)
+#define NCB_BAM_MAX_RECORD (1 << 30)
 
 struct Run {
     int64_t block_off;   // file offset of the BGZF block that holds the first record of the run
@@ -129,6 +133,10 @@ struct ncb_bam {
             return false;
         }
         b.usize = (int32_t)rd32(h + b.csize - 4);
+        if (b.usize < 0 || b.usize > 65536) {     // a BGZF member holds at most 64 KB of data
+            error = "corrupt BGZF block (ISIZE)";
+            return false;
+        }
         return true;
     }
 
@@ -165,7 +173,12 @@ struct ncb_bam {
             const size_t chunk = (blocks.size() + nt - 1) / nt;
             for (int t = 0; t < nt; ++t) {
                 const size_t a = t * chunk, b = std::min(blocks.size(), a + chunk);
-                if (a < b) pool.emplace_back(work, a, b);
+                if (a >= b) continue;
+                try {
+                    pool.emplace_back(work, a, b);
+                } catch (const std::exception &) {
+                    work(a, b);   // no thread to be had: the chunk is inflated here
+                }
             }
             for (auto &th : pool) th.join();
         }
@@ -248,16 +261,25 @@ bool build_index(ncb_bam *b) {
         if (b->error.empty()) b->error = "not a BAM file (magic)";
         return false;
     }
+    // every length field is checked before it sizes a buffer: a corrupt file must end in an error
+    // message, not in an allocation failure
     const int32_t l_text = rdi32(w + 4);
-    std::vector<uint8_t> buf((size_t)std::max(l_text, 0));
-    if (l_text > 0 && !s.read(buf.data(), buf.size())) { b->error = "truncated BAM header"; return false; }
+    if (l_text < 0) { b->error = "corrupt BAM header (l_text)"; return false; }
+    std::vector<uint8_t> buf;
+    for (int64_t left = l_text; left > 0;) {          // the header text is skipped piecewise
+        buf.resize((size_t)std::min<int64_t>(left, 1 << 20));
+        if (!s.read(buf.data(), buf.size())) { b->error = "truncated BAM header"; return false; }
+        left -= (int64_t)buf.size();
+    }
     if (!s.read(w, 4)) { b->error = "truncated BAM header"; return false; }
     const int32_t n_ref = rdi32(w);
+    if (n_ref < 0) { b->error = "corrupt BAM header (n_ref)"; return false; }
     for (int32_t i = 0; i < n_ref; ++i) {
         if (!s.read(w, 4)) { b->error = "truncated BAM reference list"; return false; }
         const int32_t l_name = rdi32(w);
+        if (l_name < 1 || l_name > (1 << 20)) { b->error = "corrupt BAM reference list (l_name)"; return false; }
         buf.resize((size_t)l_name + 4);
-        if (l_name < 1 || !s.read(buf.data(), buf.size())) { b->error = "truncated BAM reference list"; return false; }
+        if (!s.read(buf.data(), buf.size())) { b->error = "truncated BAM reference list"; return false; }
         std::string name((const char *)buf.data(), (size_t)l_name - 1);
         b->ref_index.emplace(name, i);
         b->ref_names.push_back(name);
@@ -272,7 +294,7 @@ bool build_index(ncb_bam *b) {
         if (!s.at(boff, inb)) break;   // clean end of file (or a failure flagged below)
         if (!s.read(w, 8)) { b->error = "truncated BAM record"; return false; }
         const int32_t block_size = rdi32(w), ref = rdi32(w + 4);
-        if (block_size < 32) { b->error = "corrupt BAM record (block_size)"; return false; }
+        if (block_size < 32 || block_size > NCB_BAM_MAX_RECORD) { b->error = "corrupt BAM record (block_size)"; return false; }
         buf.resize((size_t)block_size - 4);
         if (!s.read(buf.data(), buf.size())) { b->error = "truncated BAM record"; return false; }
         if (ref < 0 || ref >= n_ref) {
@@ -349,8 +371,8 @@ bool find_signal_tags(const uint8_t *p, const uint8_t *end, std::vector<int64_t>
                     const char sub = (char)p[0];
                     const uint32_t n = rd32(p + 1);
                     const int size = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+                    if ((uint64_t)n * (uint64_t)size > (uint64_t)(end - (p + 5))) return false;
                     next = p + 5 + (size_t)n * size;
-                    if (next > end) return false;
                 }
                 p = next;
                 break;
@@ -391,8 +413,17 @@ int ncb_bam_open(ncb_bam **out, const char *path, int threads) {
     }
     close(fd);
     *out = b;   // returned even on a parse failure so that the caller can read the message
-    if (!build_index(b)) {
-        if (b->error.empty()) b->error = "cannot parse BAM";
+    // nothing is thrown across the C ABI
+    try {
+        if (!build_index(b)) {
+            if (b->error.empty()) b->error = "cannot parse BAM";
+            return NCB_ERR_INVALID;
+        }
+    } catch (const std::bad_alloc &) {
+        b->error = "out of memory while indexing the BAM";
+        return NCB_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        b->error = std::string("cannot parse BAM: ") + e.what();
         return NCB_ERR_INVALID;
     }
     return NCB_OK;
@@ -433,6 +464,7 @@ int64_t ncb_bam_read_uncalled4(ncb_bam *b, int32_t ref, int64_t ref_len, int32_t
         (max_reads > 0 && ref_len > 0 && (!intensity || !dwell)))
         return NCB_ERR_INVALID;
     b->error.clear();
+    try {
     const float NaN = nanf("");
     const int shift = kit_len - kit_center;
     int64_t n_out = 0;
@@ -446,8 +478,12 @@ int64_t ncb_bam_read_uncalled4(ncb_bam *b, int32_t ref, int64_t ref_len, int32_t
         for (int64_t k = 0; k < run.n_records; ++k) {
             if (!s.read(w, 4)) { b->error = "truncated BAM record"; return NCB_ERR_INVALID; }
             const int32_t block_size = rdi32(w);
+            if (block_size < 32 || block_size > NCB_BAM_MAX_RECORD) {
+                b->error = "corrupt BAM record (block_size)";
+                return NCB_ERR_INVALID;
+            }
             rec.resize((size_t)block_size);
-            if (block_size < 32 || !s.read(rec.data(), rec.size())) {
+            if (!s.read(rec.data(), rec.size())) {
                 b->error = "truncated BAM record";
                 return NCB_ERR_INVALID;
             }
@@ -516,6 +552,13 @@ int64_t ncb_bam_read_uncalled4(ncb_bam *b, int32_t ref, int64_t ref_len, int32_t
         }
     }
     return n_out;
+    } catch (const std::bad_alloc &) {       // nothing is thrown across the C ABI
+        b->error = "out of memory while reading the BAM";
+        return NCB_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        b->error = std::string("cannot read the BAM: ") + e.what();
+        return NCB_ERR_INVALID;
+    }
 }
 
 int ncb_rows_invalid_ratio(const float *const *intensity, int64_t n_rows, int64_t n_positions,
@@ -547,7 +590,12 @@ int ncb_rows_invalid_ratio(const float *const *intensity, int64_t n_rows, int64_
         const int64_t chunk = (n_rows + nt - 1) / nt;
         for (int t = 0; t < nt; ++t) {
             const int64_t lo = t * chunk, hi = std::min(n_rows, lo + chunk);
-            if (lo < hi) pool.emplace_back(work, lo, hi);
+            if (lo >= hi) continue;
+            try {
+                pool.emplace_back(work, lo, hi);
+            } catch (const std::exception &) {
+                work(lo, hi);
+            }
         }
         for (auto &th : pool) th.join();
     }

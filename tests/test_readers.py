@@ -330,3 +330,50 @@ def test_encode_kmers_is_the_scalar_function_per_row():
     assert list(R.encode_kmers(bad, np.array([10, 60]), 5)) == [R.encode_kmer(bad[10:15]), R.encode_kmer(bad[60:65])]
     with pytest.raises(RuntimeError, match="Bad nucleotide in kmer"):
         R.encode_kmers(bad, np.array([10, 48]), 5)
+
+
+def test_corrupt_length_fields_are_errors_not_crashes(tmp_path):
+    """A length field of a corrupt file must never size a buffer: negative / absurd l_text, n_ref,
+    l_name, record block_size and BGZF ISIZE all end in an NcbError with a message (nothing is thrown
+    across the C ABI)."""
+    import struct
+    from nanocompore_b200 import _lib as L
+    rng = np.random.default_rng(21)
+
+    def bam_bytes(l_text=None, n_ref=None, l_name=None, block_size=None):
+        text = b'@HD\tVN:1.6\n'
+        out = b'BAM\1' + struct.pack('<i', len(text) if l_text is None else l_text) + text
+        out += struct.pack('<i', 1 if n_ref is None else n_ref)
+        name = b'tx\0'
+        out += struct.pack('<i', len(name) if l_name is None else l_name) + name + struct.pack('<i', 120)
+        read = SF.make_uncalled4_read(rng, 120, 'RNA002', 'r0')
+        tags = SF._aux_array('ur', 'i', read['ur']) + SF._aux_array('uc', 's', read['uc']) + \
+            SF._aux_array('ul', 's', read['ul'])
+        rec = SF._record(0, 0, 'r0', 0, tags)
+        if block_size is not None:
+            rec = struct.pack('<i', block_size) + rec[4:]
+        return out + rec
+
+    def write(path, payload, isize=None):
+        block = SF._bgzf_block(payload)
+        if isize is not None:
+            block = block[:-4] + struct.pack('<I', isize)
+        with open(path, 'wb') as f:
+            f.write(block + SF._bgzf_block(b''))
+
+    good = str(tmp_path / 'good.bam')
+    write(good, bam_bytes())
+    assert R.NativeBam(good).read_uncalled4('tx', 120, 'RNA002')[0].shape == (1, 120)
+    cases = dict(l_text=dict(l_text=-5), l_text_huge=dict(l_text=2 ** 31 - 1), n_ref=dict(n_ref=-1),
+                 n_ref_huge=dict(n_ref=2 ** 31 - 1), l_name=dict(l_name=-3), l_name_huge=dict(l_name=2 ** 30),
+                 block_size=dict(block_size=-8), block_size_huge=dict(block_size=2 ** 31 - 1))
+    for tag, kw in cases.items():
+        p = str(tmp_path / f'{tag}.bam')
+        write(p, bam_bytes(**kw))
+        with pytest.raises(L.NcbError):
+            R.NativeBam(p)
+    for isize in (0xffffffff, 70000):
+        p = str(tmp_path / f'isize_{isize}.bam')
+        write(p, bam_bytes(), isize=isize)
+        with pytest.raises(L.NcbError, match='ISIZE'):
+            R.NativeBam(p)
