@@ -288,7 +288,9 @@ int ncb_rows_invalid_ratio(const float *const *intensity, int64_t n_rows, int64_
  * Uncalled4.get_data/_copy_signal_to_tensor/_resolve_skips (uncalled4.py:57-201) for one
  * reference (transcript).  ncb_bam_open indexes the file in one pass (`threads` inflate BGZF
  * blocks in parallel); no .bai is needed.  On failure ncb_bam_open may still return a handle so
- * that ncb_bam_last_error can be read; close it. */
+ * that ncb_bam_last_error can be read; close it.  A corrupt or truncated file is an error
+ * (NCB_ERR_INVALID + message), never a crash: every length field is checked before it sizes a
+ * buffer, and no C++ exception leaves the library (NCB_ERR_NOMEM when memory runs out). */
 typedef struct ncb_bam ncb_bam;
 int ncb_bam_open(ncb_bam **out, const char *path, int threads);
 void ncb_bam_close(ncb_bam *b);
