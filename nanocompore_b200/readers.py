@@ -403,11 +403,26 @@ class TranscriptPipeline:
     ``reader``: ``Uncalled4Reader`` or ``DbReader``; ``comparator``: this package's
     ``TranscriptComparator`` (it owns the engine and assembles the frames)."""
 
-    def __init__(self, config, reader, comparator, device='cuda:0'):
+    def __init__(self, config, reader, comparator, device='cuda:0', log=None):
         self._conf = config
         self._reader = reader
         self._comparator = comparator
         self._device = device
+        worker = getattr(comparator, '_worker', None)
+        self._log = log or (worker.log if worker is not None else (lambda level, msg: None))
+        self.skipped = []          # names of the transcripts whose files could not be read
+
+    def _read_or_skip(self, transcript):
+        """run.py:481-484: an error on one transcript is logged, the transcript is skipped and the
+        worker carries on with the others."""
+        try:
+            return self.read(transcript)
+        except MemoryError:
+            raise
+        except Exception as e:
+            self._log("error", f"Encountered an error for {transcript.name}: {e}")
+            self.skipped.append(transcript.name)
+            return None
 
     def read(self, transcript):
         rows = self._reader.read(transcript.name, transcript.length)
@@ -426,10 +441,13 @@ class TranscriptPipeline:
         workers = min(len(transcripts), max(_threads() // n_samples, 1))
         if workers > 1 and getattr(self._reader, 'concurrent_reads', False):
             with ThreadPoolExecutor(max_workers=workers) as ex:
-                results = list(ex.map(self.read, transcripts))
+                results = list(ex.map(self._read_or_skip, transcripts))
         else:
-            results = [self.read(t) for t in transcripts]
-        for i, (rows, keep) in enumerate(results):
+            results = [self._read_or_skip(t) for t in transcripts]
+        for i, result in enumerate(results):
+            if result is None:
+                continue
+            rows, keep = result
             if rows.n_reads == 0:
                 continue
             live.append(i)

@@ -377,3 +377,39 @@ def test_corrupt_length_fields_are_errors_not_crashes(tmp_path):
         write(p, bam_bytes(), isize=isize)
         with pytest.raises(L.NcbError, match='ISIZE'):
             R.NativeBam(p)
+
+
+def test_pipeline_skips_a_transcript_whose_files_do_not_parse(tmp_path, monkeypatch):
+    """run.py:481-484: an error on one transcript is logged and the worker carries on.  The host half
+    of the pipeline (read -> select -> pack; no GPU) keeps the other transcripts of the batch."""
+    rng = np.random.default_rng(33)
+    refs = [('txA', 150), ('txB', 150), ('txC', 150)]
+    paths = []
+    for si, sample in enumerate(('kd1', 'kd2', 'wt1', 'wt2')):
+        reads = []
+        for ri, (name, length) in enumerate(refs):
+            for k in range(8):
+                r = SF.make_uncalled4_read(rng, length, 'RNA002', f'{sample}-{name}-{k}', ref=ri)
+                if sample == 'wt1' and name == 'txB' and k == 3:
+                    r['uc'] = r['uc'][:-7]            # signal shorter than its ur segments
+                reads.append(r)
+        p = str(tmp_path / f'{sample}.bam')
+        SF.write_bam(p, refs, reads)
+        paths.append(p)
+    cfg = bam_config(paths, max_invalid_kmers_freq=1.1, min_coverage=1)
+
+    class T:
+        def __init__(self, name, length):
+            self.name, self.length = name, length
+
+    messages = []
+    pack_rows = R.pack_rows
+    monkeypatch.setattr(R, 'pack_rows', lambda rows, offset=0, pin=False, threads=None: pack_rows(rows, offset))
+    pipe = R.TranscriptPipeline(cfg, R.Uncalled4Reader(cfg), comparator=None,
+                                log=lambda level, msg: messages.append((level, msg)))
+    transcripts, live, row_sets, masks, packed = pipe.prepare([T(n, l) for n, l in refs])
+    assert live == [0, 2] and pipe.skipped == ['txB']
+    assert len(messages) == 1 and messages[0][0] == 'error' and 'txB' in messages[0][1] and 'does not fit' in messages[0][1]
+    batch, ptx, pidx = packed
+    assert batch.n_positions == 300 and set(ptx.tolist()) == {0, 1}
+    assert [r.n_reads for r in row_sets] == [32, 32]
