@@ -1,6 +1,11 @@
 """Times builds of libncb (build/tune/*.so) on the config-3 batch shape; tuning helper.
 
-    python tests/gpu_tune.py [n_transcripts] [lib ...]
+    python -m nanocompore_b200.build -DNCB_ACC_FOLD=1 --out=build/tune/fold.so     # a variant
+    python tests/gpu_tune.py [n_transcripts] [lib ...]                              # default: build/tune/*.so
+
+One JSON line per library: milliseconds per batch of the statistics kernels, the mixture kernels and
+the exact-KS kernels (CUDA events, timed batches run on one stream), and whether the sum of all
+p-values is bit-identical to the first library's.
 """
 import glob
 import json
@@ -35,5 +40,6 @@ for lib in libs:
     chk = torch.nan_to_num(res.pvalues, nan=2.0).sum().item()
     ref = chk if ref is None else ref
     print(json.dumps(dict(lib=os.path.basename(lib), ms_position=t['ms_position'] / t['batches'],
+                          ms_stats=t['ms_stats'] / t['batches'], ms_gmm=t['ms_gmm'] / t['batches'],
                           ms_ks=t['ms_ks'] / t['batches'], positions=P, same=bool(chk == ref))), flush=True)
     eng.close()
