@@ -1,0 +1,37 @@
+"""
+The reference arm of bench.py (`--impl reference`: the CPU port on all host cores) on the CPU:
+rank 0 prints ONE JSON line with the contract's keys, every other rank exits 0 without work.
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(rank):
+    env = dict(os.environ, RANK=str(rank), WORLD_SIZE='2', LOCAL_RANK=str(rank), CUDA_VISIBLE_DEVICES='')
+    return subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+                           '--steps', '1', '--warmup', '0', '--ref-positions', '16'],
+                          env=env, capture_output=True, text=True, timeout=300)
+
+
+def test_other_ranks_exit_without_work():
+    r = run(1)
+    assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_rank0_prints_the_contract_line():
+    r = run(0)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'tested positions/sec (GMM+KS)' and d['unit'] == 'positions/s'
+    assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['n_gpus'] == 2
+    assert d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 0 and d['gpu_launches'] == 0
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] == (os.cpu_count() or 1) and cb['value'] == d['value'] and cb['sample']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert d['config']['workload'].startswith('config3')
