@@ -35,3 +35,17 @@ def test_rank0_prints_the_contract_line():
     assert cb['kind'] == 'port' and cb['cores'] == (os.cpu_count() or 1) and cb['value'] == d['value'] and cb['sample']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['config']['workload'].startswith('config3')
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm of bench.py stops with an error and
+    prints no result line."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '0',
+                        '--tx-per-step', '1', '--no-cpu-baseline'], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert not [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
