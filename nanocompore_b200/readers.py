@@ -294,6 +294,14 @@ class DbReader:
         if all(c == 0 for c in counts.values()):
             return TranscriptRows(ref_len or 0, np.empty((0, ref_len or 0), np.float32),
                                   np.empty((0, ref_len or 0), np.float32), [], [])
+        # every blob must be a float32 row of the transcript's length: the reference's assignment
+        # into its (positions, reads, 2) tensor raises otherwise (run.py:795-801)
+        row_bytes = 4 * ref_len if ref_len is not None else len(next(i for s in labels for i, _ in rows[s]))
+        for s in labels:
+            for i, d in rows[s]:
+                if len(i) != row_bytes or len(d) != row_bytes:
+                    raise ValueError(f"a signal blob of {transcript_name} in sample {s} has {len(i)} / {len(d)} bytes, "
+                                     f"expected {row_bytes}")
         # blobs are float32 rows of length ref_len (database.py:69-76); one copy each into a
         # contiguous (R, P) block, samples in config order (run.py:820-826)
         inten = np.frombuffer(b''.join(i for s in labels for i, _ in rows[s]), dtype=np.float32)

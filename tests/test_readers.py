@@ -413,3 +413,27 @@ def test_pipeline_skips_a_transcript_whose_files_do_not_parse(tmp_path, monkeypa
     batch, ptx, pidx = packed
     assert batch.n_positions == 300 and set(ptx.tolist()) == {0, 1}
     assert [r.n_reads for r in row_sets] == [32, 32]
+
+
+def test_db_reader_rejects_blobs_of_the_wrong_length(tmp_path):
+    """Two blobs whose lengths are off by +1 / -1 positions add up to the right total: only a per-blob
+    check keeps the rows aligned (the reference's tensor assignment raises, run.py:795-801)."""
+    rng = np.random.default_rng(8)
+    P = 40
+    paths = {}
+    for sample in ('kd1', 'kd2', 'wt1', 'wt2'):
+        reads = [(f'{sample}{k}', k, 0.0) for k in range(2)]
+        lens = (P + 1, P - 1) if sample == 'wt2' else (P, P)
+        signal = [(1, k, rng.normal(100, 5, n).astype(np.float32), rng.random(n).astype(np.float32))
+                  for k, n in enumerate(lens)]
+        paths[sample] = str(tmp_path / f'{sample}.db')
+        SF.write_db(paths[sample], [('tx1', 1)], reads, signal)
+    cfg = PathConfig(dict(data={'kd': {'kd1': {'db': paths['kd1']}, 'kd2': {'db': paths['kd2']}},
+                                'wt': {'wt1': {'db': paths['wt1']}, 'wt2': {'db': paths['wt2']}}},
+                          depleted_condition='kd', max_invalid_kmers_freq=0.1))
+    reader = R.DbReader(cfg)
+    with pytest.raises(ValueError, match='wt2'):
+        reader.read('tx1', P)
+    with pytest.raises(ValueError, match='wt2'):
+        reader.read('tx1')
+    reader.close()
