@@ -188,7 +188,7 @@ class NativeBam:
         klen, kcenter = kit_geometry(kit)
         i = self._lib.ncb_bam_reference_index(self._h, reference.encode())
         cap = 0 if i < 0 else int(self._lib.ncb_bam_reference_records(self._h, i))
-        stride = 96
+        stride = 256       # a BAM read name has at most 254 characters + NUL: never truncated
         inten = np.empty((cap, ref_len), dtype=np.float32)
         dwell = np.empty((cap, ref_len), dtype=np.float32)
         names = np.zeros((max(cap, 1), stride), dtype=np.uint8)

@@ -437,3 +437,21 @@ def test_db_reader_rejects_blobs_of_the_wrong_length(tmp_path):
     with pytest.raises(ValueError, match='wt2'):
         reader.read('tx1')
     reader.close()
+
+
+def test_long_read_names_are_not_truncated(tmp_path):
+    """Reads are ordered by read id (run.py:698-700): names that differ only after the 200th character
+    must still sort by their full text."""
+    rng = np.random.default_rng(4)
+    refs = [('tx', 100)]
+    stem = 'x' * 230
+    paths = []
+    for sample in ('kd1', 'kd2', 'wt1', 'wt2'):
+        reads = [SF.make_uncalled4_read(rng, 100, 'RNA002', f'{stem}-{sample}-{k}', n_segments=1) for k in (2, 0, 1)]
+        p = str(tmp_path / f'{sample}_long.bam')
+        SF.write_bam(p, refs, reads)
+        paths.append(p)
+    rows = R.Uncalled4Reader(bam_config(paths, max_invalid_kmers_freq=1.1)).read('tx', 100)
+    names = list(rows.read_names)
+    assert len(names) == 12 and all(len(n) > 230 for n in names) and names == sorted(names)
+    assert names[0] == f'{stem}-kd1-0' and names[-1] == f'{stem}-wt2-2'
