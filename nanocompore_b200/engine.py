@@ -92,7 +92,10 @@ def pack_csr(transcripts, pin=False, threads=None):
     for data, samples, conditions in transcripts:
         data = np.ascontiguousarray(data, dtype=np.float32)
         assert data.ndim == 3 and data.shape[2] >= 2
-        items.append((data, make_labels(samples, conditions)))
+        lab = make_labels(samples, conditions)
+        if lab.shape != (data.shape[1],):
+            raise ValueError(f"{data.shape[1]} reads in the tensor, {lab.size} sample / condition ids")
+        items.append((data, lab))
     counts = []
     for data, lab in items:
         c = np.empty(data.shape[0], dtype=np.int64)
@@ -307,6 +310,8 @@ class Engine:
         on_dev = data.is_cuda
         assert labels.is_cuda == on_dev
         P, R, V = data.shape
+        if labels.numel() != R:
+            raise ValueError(f"{R} reads in the tensor, {labels.numel()} labels")
         if results is None:
             results = Results(P, self.opts.n_samples, self.device if on_dev else None, diagnostics,
                               pinned=False)

@@ -52,3 +52,13 @@ def test_rejects_bad_arguments():
     assert lib.ncb_pack_count(None, 4, 2, 2, c.ctypes.data, 1) == L.NCB_ERR_INVALID
     d = np.zeros((4, 2, 1), dtype=np.float32)
     assert lib.ncb_pack_count(d.ctypes.data, 4, 2, 1, c.ctypes.data, 1) == L.NCB_ERR_INVALID
+
+
+def test_pack_csr_rejects_mismatched_ids():
+    import pytest
+    from nanocompore_b200.engine import pack_csr
+    data = np.zeros((3, 5, 2), dtype=np.float32)
+    with pytest.raises(ValueError, match='5 reads'):
+        pack_csr([(data, np.zeros(4, dtype=np.int64), np.zeros(4, dtype=np.int64))])
+    with pytest.raises(ValueError):
+        pack_csr([(data, np.zeros(5, dtype=np.int64), np.zeros(4, dtype=np.int64))])
