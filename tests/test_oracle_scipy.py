@@ -73,3 +73,39 @@ def test_bh_properties():
     assert stats.false_discovery_control(p, method='bh') == pytest.approx(q, rel=1e-12)
     a = auto_qvalues(np.array([0.01, 0.5, np.nan, 0.2]), np.array(['KS', 'GMM', 'KS', 'KS']))
     assert np.isnan(a[2]) and a[1] == pytest.approx(0.5 * 4)
+
+
+def test_gmm_definition_on_the_reference_test_arrays_against_scikit_learn():
+    """The arrays of the reference's tests/test_comparisons.py:464-504 (default_rng(42), 1 x 100 x 2;
+    second half shifted by +3).  oracle/gmm.py follows scikit-learn's GaussianMixture(covariance_type=
+    'full'): same BICs as scikit-learn 1.9 with its k-means initialisation -- 536.34
+    vs ~560 on the unimodal array (p must be NaN), 718.48 vs 693.69 on the shifted one -- table + 1 =
+    [[51, 1], [1, 51]] and chi-squared p = 7.28e-22, the known answers of the survey's probe."""
+    from sklearn.mixture import GaussianMixture
+    from oracle.gmm import GMM
+    from oracle.gmm_test import gmm_test_split
+    rng = np.random.default_rng(42)
+    X = rng.standard_normal((1, 100, 2))
+    samples, cond = np.repeat([0, 1, 2, 3], 25), np.repeat([0, 1], 50)
+    ids = {'kd1': 0, 'kd2': 1, 'wt1': 2, 'wt2': 3}
+
+    def sk_bic(x, k):
+        return GaussianMixture(k, covariance_type='full', tol=1e-3, reg_covar=1e-6, max_iter=100,
+                               random_state=42).fit(x).bic(x)
+
+    # unimodal: one component wins, no p-value
+    b1, b2 = float(GMM(1).fit(X).bic(X)[0]), float(GMM(2).fit(X).bic(X)[0])
+    assert abs(b1 - 536.3424) < 1e-3 and abs(b1 - sk_bic(X[0], 1)) < 1e-6 * b1
+    assert b2 > b1 and 555 < b2 < 565 and 555 < sk_bic(X[0], 2) < 565
+    out = gmm_test_split(X, samples, cond, ids, 0)
+    assert np.isnan(out['GMM_chi2_pvalue'][0]) and np.isnan(out['GMM_LOR'][0])
+    # two clusters
+    Y = X.copy()
+    Y[:, 50:, :] += 3
+    out, fit = gmm_test_split(Y, samples, cond, ids, 0, return_fit=True)
+    y32 = Y[0].astype(np.float32).astype(np.float64)          # the reference hands float32 to the mixture
+    assert abs(fit['bic1'][0] - 718.4815) < 1e-3 and abs(fit['bic2'][0] - 693.6874) < 1e-3
+    assert abs(fit['bic2'][0] - sk_bic(y32, 2)) < 1e-6 * 693.0 and abs(fit['bic1'][0] - sk_bic(y32, 1)) < 1e-6 * 718.0
+    assert sorted((fit['cont'][0] + 1).ravel().tolist()) == [1.0, 1.0, 51.0, 51.0]
+    assert abs(out['GMM_chi2_pvalue'][0] / 7.27672954e-22 - 1) < 1e-6
+    assert abs(abs(float(out['GMM_LOR'][0])) - 7.864) < 1e-3
