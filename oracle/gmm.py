@@ -164,6 +164,8 @@ class GMM:
                     p1 = np.where(live[:, None], q1, p1)
                 R = np.stack([assign, ~assign], axis=2).astype(self.wd) * vf[:, :, None]
                 w, mu, cov = self._moments(Xz, R)
+                # the parameters EM starts from (tests hand them to scikit-learn as *_init)
+                self.init_ = (w.copy(), mu.copy(), cov.copy())
 
                 active = self._ok.copy()
                 prev = np.full(B, -np.inf)

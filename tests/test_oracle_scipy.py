@@ -109,3 +109,40 @@ def test_gmm_definition_on_the_reference_test_arrays_against_scikit_learn():
     assert sorted((fit['cont'][0] + 1).ravel().tolist()) == [1.0, 1.0, 51.0, 51.0]
     assert abs(out['GMM_chi2_pvalue'][0] / 7.27672954e-22 - 1) < 1e-6
     assert abs(abs(float(out['GMM_LOR'][0])) - 7.864) < 1e-3
+
+
+def test_em_equals_scikit_learn_from_the_same_start():
+    """The EM part of the definition, separated from the initialisation: started from the oracle's own
+    initial parameters (weights_init / means_init / precisions_init), scikit-learn's GaussianMixture
+    performs the same number of iterations and ends with the same BIC and the same hard assignment
+    on every position -- ordinary, tiny (4-12 reads) and well separated ones."""
+    import warnings
+    from sklearn.mixture import GaussianMixture
+    from oracle.gmm import GMM
+    rng = np.random.default_rng(7)
+    B, N = 240, 160
+    X = np.full((B, N, 2), np.nan)
+    for b in range(B):
+        m = int(rng.integers(4, 13)) if b % 3 == 0 else int(rng.integers(30, N + 1))
+        pts = rng.standard_normal((m, 2))
+        if b % 2:
+            pts[: m // 3] += rng.normal(0, 2.5, 2)
+        pts = (pts - pts.mean(0)) / pts.std(0)
+        X[b, rng.permutation(N)[:m]] = pts
+    g = GMM(2).fit(X)
+    w0, mu0, cov0 = g.init_
+    bic = np.asarray(g.bic(X))
+    pred = g.predict_proba(X).argmax(2)
+    checked = 0
+    for b in range(B):
+        v = X[b][~np.isnan(X[b]).any(1)]
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')       # scikit-learn warns when max_iter is reached
+            sk = GaussianMixture(2, covariance_type='full', tol=1e-3, reg_covar=1e-6, max_iter=100,
+                                 weights_init=w0[b], means_init=mu0[b],
+                                 precisions_init=np.linalg.inv(cov0[b])).fit(v)
+        assert sk.n_iter_ == g.n_iter[b], (b, sk.n_iter_, g.n_iter[b])
+        assert abs(sk.bic(v) - bic[b]) <= 1e-7 * abs(bic[b]) + 1e-7, (b, sk.bic(v), bic[b])
+        assert (sk.predict(v) == pred[b][~np.isnan(X[b]).any(1)]).all(), b
+        checked += 1
+    assert checked == B
