@@ -111,22 +111,24 @@ def test_gmm_definition_on_the_reference_test_arrays_against_scikit_learn():
     assert abs(abs(float(out['GMM_LOR'][0])) - 7.864) < 1e-3
 
 
-def test_em_equals_scikit_learn_from_the_same_start():
+@pytest.mark.parametrize('D', [2, 3])
+def test_em_equals_scikit_learn_from_the_same_start(D):
     """The EM part of the definition, separated from the initialisation: started from the oracle's own
     initial parameters (weights_init / means_init / precisions_init), scikit-learn's GaussianMixture
     performs the same number of iterations and ends with the same BIC and the same hard assignment
-    on every position -- ordinary, tiny (4-12 reads) and well separated ones."""
+    on every position -- ordinary, tiny (up to 12 reads) and well separated ones, in 2 and in 3
+    variables (the motor-dwell fit)."""
     import warnings
     from sklearn.mixture import GaussianMixture
     from oracle.gmm import GMM
-    rng = np.random.default_rng(7)
+    rng = np.random.default_rng(7 + D)
     B, N = 240, 160
-    X = np.full((B, N, 2), np.nan)
+    X = np.full((B, N, D), np.nan)
     for b in range(B):
-        m = int(rng.integers(4, 13)) if b % 3 == 0 else int(rng.integers(30, N + 1))
-        pts = rng.standard_normal((m, 2))
+        m = int(rng.integers(2 * D, 13)) if b % 3 == 0 else int(rng.integers(30, N + 1))
+        pts = rng.standard_normal((m, D))
         if b % 2:
-            pts[: m // 3] += rng.normal(0, 2.5, 2)
+            pts[: m // 3] += rng.normal(0, 2.5, D)
         pts = (pts - pts.mean(0)) / pts.std(0)
         X[b, rng.permutation(N)[:m]] = pts
     g = GMM(2).fit(X)
