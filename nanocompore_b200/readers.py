@@ -171,7 +171,7 @@ class NativeBam:
             self.close()
             raise L.NcbError(rc, f"{self.path}: {msg}")
         n = self._lib.ncb_bam_n_references(self._h)
-        self.references = [self._lib.ncb_bam_reference_name(self._h, i).decode() for i in range(n)]
+        self.references = [self._lib.ncb_bam_reference_name(self._h, i).decode(errors='replace') for i in range(n)]
         self.lengths = [int(self._lib.ncb_bam_reference_length(self._h, i)) for i in range(n)]
 
     def count(self, reference):
@@ -198,7 +198,7 @@ class NativeBam:
                                                  dwell.ctypes.data, names.ctypes.data, stride, cap)
             if n < 0:
                 raise L.NcbError(int(n), self._lib.ncb_bam_last_error(self._h).decode(errors='replace'))
-        read_names = [bytes(names[k]).split(b'\0', 1)[0].decode() for k in range(n)]
+        read_names = [bytes(names[k]).split(b'\0', 1)[0].decode(errors='replace') for k in range(n)]
         return inten[:n], dwell[:n], read_names
 
     def close(self):

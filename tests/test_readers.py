@@ -455,3 +455,15 @@ def test_long_read_names_are_not_truncated(tmp_path):
     names = list(rows.read_names)
     assert len(names) == 12 and all(len(n) > 230 for n in names) and names == sorted(names)
     assert names[0] == f'{stem}-kd1-0' and names[-1] == f'{stem}-wt2-2'
+
+
+def test_damaged_bams_never_crash_the_reader():
+    """tests/fuzz_bam.py in a child process (a crash must fail this test, not end the test run):
+    250 damaged copies of a valid BAM, each read back -- a result or an NcbError, never a crash."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'fuzz_bam.py'), '11', '250'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-1500:])
+    words = r.stdout.split()
+    assert words[0] == 'survived' and int(words[1]) + int(words[3]) == 250 and int(words[3]) > 50
