@@ -496,8 +496,9 @@ int64_t ncb_bam_read_uncalled4(ncb_bam *b, int32_t ref, int64_t ref_len, int32_t
             if (n_out >= max_reads) { b->error = "more primary reads than the caller's capacity"; return NCB_ERR_INVALID; }
             const uint8_t *p = r + 32;
             const uint8_t *end = r + block_size;
-            const size_t fixed = (size_t)l_read_name + 4u * n_cigar + (size_t)(l_seq + 1) / 2 + (size_t)l_seq;
-            if (l_seq < 0 || p + fixed > end) { b->error = "corrupt BAM record"; return NCB_ERR_INVALID; }
+            if (l_seq < 0) { b->error = "corrupt BAM record (l_seq)"; return NCB_ERR_INVALID; }
+            const size_t fixed = (size_t)l_read_name + 4u * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+            if (fixed > (size_t)(end - p)) { b->error = "corrupt BAM record"; return NCB_ERR_INVALID; }
             char *name = names + n_out * name_stride;
             memset(name, 0, (size_t)name_stride);
             memcpy(name, p, (size_t)std::min(l_read_name > 0 ? l_read_name - 1 : 0, name_stride - 1));

@@ -5,7 +5,10 @@ then a byte of the compressed file -- and read back.  Every outcome must be a re
 with a message; a crash (wrong bounds check, exception across the C ABI) ends the process, which is
 what tests/test_readers.py::test_damaged_bams_never_crash_the_reader looks for.
 
-    python tests/fuzz_bam.py [seed] [files]
+    python tests/fuzz_bam.py [seed] [files] [--keep DIR]
+
+``--keep DIR`` writes the damaged files to DIR and does not read them (input of the sanitizer harness
+tests/csrc/asan_bam_harness.cpp).
 """
 import os
 import struct
@@ -58,8 +61,10 @@ def damaged(rng, stream):
 def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     n_files = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+    keep = sys.argv[sys.argv.index('--keep') + 1] if '--keep' in sys.argv else None
     rng = np.random.default_rng(seed)
-    tmp = tempfile.mkdtemp()
+    tmp = keep or tempfile.mkdtemp()
+    os.makedirs(tmp, exist_ok=True)
     stream = valid_stream(rng)
     survived = errors = 0
     for it in range(n_files):
@@ -73,6 +78,8 @@ def main():
             raw = bytearray(open(path, 'rb').read())
             raw[int(rng.integers(0, len(raw)))] = int(rng.integers(0, 256))
             open(path, 'wb').write(raw)
+        if keep:
+            continue
         try:
             bam = R.NativeBam(path, threads=2)
             for name, length in REFS:
