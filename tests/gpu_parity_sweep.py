@@ -44,8 +44,6 @@ def job_inputs(seed, P, n, q):
 def gpu_results(jobs):
     import torch
     from nanocompore_b200.engine import Engine, make_labels
-    from oracle import prep as oprep
-    from nanocompore_b200.synthetic import make_transcript
     eng = Engine(0, tests=('KS', 'MW', 'TT', 'GMM'), with_logit=not MOTOR, **(dict(min_coverage=0) if MOTOR else {}))
     out = []
     if CSR:
