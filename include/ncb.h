@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NCB_ABI_VERSION 1
+#define NCB_ABI_VERSION 2
 
 typedef struct ncb_handle ncb_handle;
 
@@ -39,7 +39,10 @@ typedef enum {
     NCB_ERR_INVALID = -1,      /* bad argument                                          */
     NCB_ERR_CUDA = -2,         /* CUDA runtime error (message in ncb_last_error)        */
     NCB_ERR_NOMEM = -3,        /* device/pinned allocation failed (maps to torch.OutOfMemoryError) */
-    NCB_ERR_TOO_MANY_READS = -4 /* a position has more valid reads than NCB_MAX_READS   */
+    NCB_ERR_TOO_MANY_READS = -4 /* returned by ncb_wait: a position of a batch since the last ncb_wait holds
+                                   more entries than NCB_MAX_READS (or than ncb_batch.n_reads declared); that
+                                   position has status NCB_POS_TOO_MANY_READS and the NaN / 0 defaults in its
+                                   result row, every other position of the batch is complete             */
 } ncb_status;
 
 /* Most valid reads one position may hold (the reference caps at 5000 per condition,
@@ -65,8 +68,13 @@ enum { NCB_MEM_HOST = 0, NCB_MEM_DEVICE = 1 };
 
 /* input layout */
 enum {
-    NCB_LAYOUT_CSR = 0,   /* ragged: pos_offsets[P+1], signal[E][2], label[E]             */
-    NCB_LAYOUT_DENSE = 1  /* the reference's tensor: signal[P][R][V] with NaN, label[R]   */
+    NCB_LAYOUT_CSR = 0,   /* ragged: pos_offsets[P+1], signal float32[E][V], label[E]     */
+    NCB_LAYOUT_DENSE = 1, /* the reference's tensor: signal[P][R][V] with NaN, label[R]   */
+    NCB_LAYOUT_CSR_I16 = 2 /* ragged like NCB_LAYOUT_CSR with the entries as int16 codes: signal points at
+                             int16[E][V], value = (float)code, -32768 = NaN.  This is what Uncalled4 stores
+                             (tags uc / ul are int16 arrays copied into the float32 tensor as they are,
+                             uncalled4.py:118-192, -32768 -> NaN at 103-107), so for that input the layout is
+                             lossless at 5 instead of 9 bytes per entry on the host-to-device link          */
 };
 
 /* per-position status bits; the row is dropped by the host mirror when
@@ -75,7 +83,8 @@ enum {
     NCB_POS_OK = 0,
     NCB_POS_LOW_COVERAGE = 1,   /* run.py:511-515                                        */
     NCB_POS_BAD_STD = 2,        /* comparisons.py:108-120: std NaN or 0 after the filter */
-    NCB_POS_TOO_MANY_READS = 4, /* more than NCB_MAX_READS valid reads: ncb_wait fails   */
+    NCB_POS_TOO_MANY_READS = 4, /* more than NCB_MAX_READS entries (or than ncb_batch.n_reads): the row holds
+                                   the defaults and ncb_wait returns NCB_ERR_TOO_MANY_READS */
     NCB_POS_DROP_MASK = 7,
     NCB_POS_AUTO_GMM = 256,     /* informational, with NCB_TEST_AUTO: the automatic test of
                                    this position is GMM (coverage >= 500), else KS       */
@@ -109,7 +118,8 @@ typedef struct {
     int64_t n_positions;        /* P                                                     */
     int64_t n_entries;          /* CSR: E = pos_offsets[P]; dense: P*R                   */
     const int64_t *pos_offsets; /* CSR: [P+1]; dense: NULL                               */
-    const float *signal;        /* CSR: [E][V] {intensity, dwell[, motor dwell]}; dense: [P][R][V] */
+    const void *signal;         /* CSR: float32[E][V] {intensity, dwell[, motor dwell]}; CSR_I16: int16[E][V];
+                                   dense: float32[P][R][V]                                */
     const uint8_t *label;       /* CSR: [E]; dense: [R]                                  */
     int32_t n_reads;            /* dense: R.  CSR: an upper bound on the entries of a position if the
                                    packer knows one (ncb_pack_* callers do), 0 = unknown.  The kernels of
@@ -168,6 +178,13 @@ enum {
     NCB_DF_ROWS = 17
 };
 
+/* Host results (memory == NCB_MEM_HOST): only the rows the configured tests write are copied back --
+ * status; the p-value rows of the tests in ncb_opts.tests (GMM_LOGIT rows with NCB_TEST_LOGIT); stats rows
+ * 0..11 (+ GMM_LOR with a mixture test, + the motor rows of a 3-variable batch); counts with a mixture test
+ * and cluster_counts != NCB_COUNTS_NONE.  Rows of tests that were not asked for are left as the caller's
+ * buffer had them (fill it with NaN once to read them as "not tested"); ncb_results_host_bytes() gives the
+ * bytes a call copies.  Device results (NCB_MEM_DEVICE): every row of every array is written (NaN / 0 where
+ * a test did not run). */
 typedef struct {
     int32_t memory;        /* NCB_MEM_*: where the arrays below live                      */
     int32_t reserved;
@@ -207,6 +224,9 @@ const char *ncb_last_error(const ncb_handle *h);
  * NCB_MEM_DEVICE buffers nothing is copied and the kernels are only enqueued.        */
 int ncb_compare(ncb_handle *h, const ncb_batch *batch, ncb_results *results, void *stream);
 int ncb_wait(ncb_handle *h, void *stream);
+/* Bytes ncb_compare copies device->host for a batch of P positions with host results (see ncb_results);
+ * n_vars as in ncb_batch, with_counts = results->counts != NULL. */
+int64_t ncb_results_host_bytes(const ncb_handle *h, int64_t n_positions, int32_t n_vars, int with_counts);
 
 /* --- unit entry points (each is one stage of ncb_compare, exposed for parity tests) */
 
@@ -257,6 +277,13 @@ int ncb_pack_count(const float *data, int64_t n_positions, int32_t n_reads, int3
 int ncb_pack_fill(const float *data, const uint8_t *label, int64_t n_positions, int32_t n_reads,
                   int32_t n_vars, const int64_t *pos_offsets, float *signal_out, uint8_t *label_out,
                   int threads);
+/* Same, writing NCB_LAYOUT_CSR_I16 entries (int16[E][2]).  Every number of the tensor must be an integer in
+ * [-32767, 32767] (Uncalled4 input: the float32 tensor holds int16 tag values, uncalled4.py:118-192); NaN
+ * becomes -32768.  Returns NCB_ERR_INVALID, with nothing usable written, when a value is not representable
+ * (the caller then packs float32 entries with ncb_pack_fill). */
+int ncb_pack_fill_i16(const float *data, const uint8_t *label, int64_t n_positions, int32_t n_reads,
+                      int32_t n_vars, const int64_t *pos_offsets, int16_t *signal_out, uint8_t *label_out,
+                      int threads);
 
 /* --- transcript readers (host code) ---------------------------------------
  * Planar rows: one read = intensity[n_positions] + dwell[n_positions] float32, NaN where the
@@ -279,6 +306,12 @@ int ncb_pack_rows_fill(const float *const *intensity, const float *const *dwell,
                        const uint8_t *row_label, int64_t n_rows, int64_t n_positions,
                        int32_t motor_offset, const int64_t *pos_offsets, float *signal_out,
                        uint8_t *label_out, int threads);
+/* ncb_pack_rows_fill writing NCB_LAYOUT_CSR_I16 entries (int16[E][2 or 3]); representability rule and
+ * return value as ncb_pack_fill_i16. */
+int ncb_pack_rows_fill_i16(const float *const *intensity, const float *const *dwell,
+                           const uint8_t *row_label, int64_t n_rows, int64_t n_positions,
+                           int32_t motor_offset, const int64_t *pos_offsets, int16_t *signal_out,
+                           uint8_t *label_out, int threads);
 /* common.get_reads_invalid_ratio (common.py:298-329): per row, the share of positions between
  * its first and last valid intensity that are NaN; NaN for a row without any valid position. */
 int ncb_rows_invalid_ratio(const float *const *intensity, int64_t n_rows, int64_t n_positions,

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # NCB_LIB_PATH lets a tuning run load an experimental build of the same ABI
 LIB_PATH = os.environ.get('NCB_LIB_PATH') or os.path.join(HERE, 'libncb.so')
 
-NCB_ABI_VERSION = 1
+NCB_ABI_VERSION = 2
 NCB_MAX_READS = 10240
 NCB_MAX_SAMPLES = 64
 
@@ -19,7 +19,7 @@ NCB_OK, NCB_ERR_INVALID, NCB_ERR_CUDA, NCB_ERR_NOMEM, NCB_ERR_TOO_MANY_READS = 0
 NCB_TEST_KS, NCB_TEST_MW, NCB_TEST_TT, NCB_TEST_GMM, NCB_TEST_LOGIT, NCB_TEST_AUTO = 1, 2, 4, 8, 16, 32
 NCB_COUNTS_NONE, NCB_COUNTS_HARD, NCB_COUNTS_SOFT = 0, 1, 2
 NCB_MEM_HOST, NCB_MEM_DEVICE = 0, 1
-NCB_LAYOUT_CSR, NCB_LAYOUT_DENSE = 0, 1
+NCB_LAYOUT_CSR, NCB_LAYOUT_DENSE, NCB_LAYOUT_CSR_I16 = 0, 1, 2
 
 NCB_POS_LOW_COVERAGE, NCB_POS_BAD_STD, NCB_POS_TOO_MANY_READS = 1, 2, 4
 NCB_POS_DROP_MASK = 7
@@ -47,7 +47,8 @@ DF = dict(BIC1=0, BIC2=1, W0=2, MU0_X=3, MU0_Y=4, C0_XX=5, C0_XY=6, C0_YY=7,
 NCB_DF_ROWS = 17
 
 EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
-           'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
+           'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_results_host_bytes',
+           'ncb_pack_fill_i16', 'ncb_pack_rows_fill_i16', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
            'ncb_context_combine',
            'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals',
            'ncb_pack_count', 'ncb_pack_fill', 'ncb_pack_rows_count', 'ncb_pack_rows_fill',
@@ -131,6 +132,12 @@ def load(path=None):
     lib.ncb_pack_count.restype = C.c_int
     lib.ncb_pack_fill.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, C.c_int]
     lib.ncb_pack_fill.restype = C.c_int
+    lib.ncb_pack_fill_i16.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, C.c_int]
+    lib.ncb_pack_fill_i16.restype = C.c_int
+    lib.ncb_pack_rows_fill_i16.argtypes = [vp, vp, vp, i64, i64, i32, vp, vp, vp, C.c_int]
+    lib.ncb_pack_rows_fill_i16.restype = C.c_int
+    lib.ncb_results_host_bytes.argtypes = [vp, i64, i32, C.c_int]
+    lib.ncb_results_host_bytes.restype = i64
     lib.ncb_pack_rows_count.argtypes = [vp, vp, i64, i64, i32, vp, C.c_int]
     lib.ncb_pack_rows_count.restype = C.c_int
     lib.ncb_pack_rows_fill.argtypes = [vp, vp, vp, i64, i64, i32, vp, vp, vp, C.c_int]

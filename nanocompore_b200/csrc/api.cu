@@ -29,6 +29,9 @@ struct ncb_handle {
     // stream next to the mixture kernels (fork after the statistics phase, join before the results)
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // sticky NCB_POS_TOO_MANY_READS flag: mapped pinned host word the kernels OR into, read (and
+    // cleared) by ncb_wait after the stream has drained
+    int32_t *flag_host = nullptr, *flag_dev = nullptr;
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
@@ -39,6 +42,22 @@ struct ncb_handle {
     DevBuf unit_a, unit_b, unit_c, unit_d;
     DevBuf ctx_tx, ctx_track, ctx_idx, ctx_p, ctx_tracks, ctx_out, ctx_status;
 };
+
+// Entry points select the handle's device for their own calls and put the caller's current
+// device back on return (a multi-GPU torch process keeps its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t enter(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev == device) return cudaSuccess;
+        cudaError_t e = cudaSetDevice(device);
+        changed = e == cudaSuccess && prev >= 0;
+        return e;
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h) DeviceGuard guard_; CK(guard_.enter((h)->device))
 
 static int fail(ncb_handle *h, int code, const char *what, cudaError_t e = cudaSuccess) {
     if (h) {
@@ -149,7 +168,8 @@ int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
         return NCB_ERR_CUDA;
     }
     h->device = device;
-    if (cudaSetDevice(device) != cudaSuccess) { delete h; return NCB_ERR_CUDA; }
+    DeviceGuard guard;
+    if (guard.enter(device) != cudaSuccess) { delete h; return NCB_ERR_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return NCB_ERR_CUDA; }
     h->sm_count = prop.multiProcessorCount;
@@ -159,21 +179,21 @@ int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
         delete h;
         return NCB_ERR_CUDA;
     }
-    if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        fprintf(stderr, "libncb: cannot create streams on device %d (%s)\n", device, cudaGetErrorString(cudaGetLastError()));
-        delete h;
-        return NCB_ERR_CUDA;
-    }
     // table of reciprocals for the exact-KS kernels, filled once
-    if (ensure(h, h->kw_rtab, NCB_KS_RTAB_SIZE * sizeof(double)) != NCB_OK ||
-        ncb_launch_ks_rtab((double *)h->kw_rtab.ptr, nullptr) < 0 || cudaDeviceSynchronize() != cudaSuccess) {
+    const bool ok =
+        cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+        cudaHostAlloc((void **)&h->flag_host, sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer((void **)&h->flag_dev, h->flag_host, 0) == cudaSuccess &&
+        ensure(h, h->kw_rtab, NCB_KS_RTAB_SIZE * sizeof(double)) == NCB_OK &&
+        ncb_launch_ks_rtab((double *)h->kw_rtab.ptr, nullptr) >= 0 && cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) {
         fprintf(stderr, "libncb: cannot set up device %d (%s)\n", device, cudaGetErrorString(cudaGetLastError()));
-        release(h->kw_rtab);
-        delete h;
+        ncb_destroy(h);   // releases whatever was created
         return NCB_ERR_CUDA;
     }
+    *h->flag_host = 0;
     const char *t = getenv("NCB_TIMING");
     h->timing = (t && t[0] == '1') ? 1 : 0;
     *out = h;
@@ -190,7 +210,8 @@ int ncb_set_opts(ncb_handle *h, const ncb_opts *opts) {
 
 void ncb_destroy(ncb_handle *h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard;
+    guard.enter(h->device);
     DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
                      &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
                      &h->ks_h, &h->zbuf, &h->gmm_n, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
@@ -202,6 +223,7 @@ void ncb_destroy(ncb_handle *h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->flag_host) cudaFreeHost(h->flag_host);
     delete h;
 }
 
@@ -230,9 +252,10 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     if (P < 0 || P > 0x7fffffffLL / 2) return fail(h, NCB_ERR_INVALID, "ncb_compare: n_positions out of range");
     if (P == 0) return NCB_OK;
     if (!res->status || !res->pvalues || !res->stats) return fail(h, NCB_ERR_INVALID, "ncb_compare: status, pvalues and stats are required");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const ncb_opts &o = h->opts;
-    const bool csr = b->layout == NCB_LAYOUT_CSR;
+    const bool i16 = b->layout == NCB_LAYOUT_CSR_I16;
+    const bool csr = b->layout == NCB_LAYOUT_CSR || i16;
     int64_t E;
     size_t label_bytes;
     int n_vars;
@@ -252,7 +275,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
         return fail(h, NCB_ERR_INVALID, "ncb_compare: unknown layout");
     }
     if (E > 0 && (!b->signal || !b->label)) return fail(h, NCB_ERR_INVALID, "ncb_compare: null signal or label");
-    const size_t signal_bytes = (size_t)E * n_vars * sizeof(float);
+    const size_t signal_bytes = (size_t)E * n_vars * (i16 ? sizeof(int16_t) : sizeof(float));
     const int S = o.n_samples;
 
     NcbDeviceArgs a;
@@ -261,6 +284,8 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     a.n_reads = csr ? 0 : b->n_reads;
     a.max_entries = b->n_reads > 0 ? b->n_reads : 0;
     a.n_vars = n_vars;
+    a.signal_i16 = i16 ? 1 : 0;
+    a.error_flag = h->flag_dev;
     a.tests = o.tests;
     a.n_samples = S;
     a.depleted_condition = o.depleted_condition;
@@ -271,7 +296,9 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     a.em_tol = o.em_tol;
     a.reg_covar = o.reg_covar;
 
-    const bool time_it = h->timing != 0;
+    // the timing log holds at most NCB_TIMING_LOG_MAX batches: later batches run untimed (a process
+    // that leaves NCB_TIMING=1 on for a whole run does not accumulate events without bound)
+    const bool time_it = h->timing != 0 && h->ev_log.size() < 5 * (size_t)NCB_TIMING_LOG_MAX;
     if (time_it) {
         for (int i = 0; i < 5; ++i) {
             cudaEvent_t e;
@@ -302,7 +329,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
             a.pos_offsets = (const int64_t *)h->in_offsets.ptr;
         }
     } else if (b->memory == NCB_MEM_DEVICE) {
-        a.signal = b->signal;
+        a.signal = (const float *)b->signal;
         a.label = b->label;
         a.pos_offsets = csr ? b->pos_offsets : nullptr;
     } else {
@@ -405,21 +432,67 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     h->timed = time_it;
 
     // ---- results -----------------------------------------------------------------------
+    // Host results: only the rows the configured tests write are copied (the others keep whatever the
+    // caller's buffer held -- ncb.h); the rows of one column group are contiguous, so every group is
+    // one copy.
     if (out_host) {
         CK(cudaMemcpyAsync(res->status, a.status, b_status, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(res->pvalues, a.pvalues, b_pv, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(res->stats, a.stats, b_st, cudaMemcpyDeviceToHost, s));
-        if (a.counts) CK(cudaMemcpyAsync(res->counts, a.counts, b_cnt, cudaMemcpyDeviceToHost, s));
+        auto rows_pv = [&](int r0, int r1) {   // pvalues rows [r0, r1)
+            return cudaMemcpyAsync(res->pvalues + (size_t)r0 * P, a.pvalues + (size_t)r0 * P,
+                                   (size_t)(r1 - r0) * P * sizeof(double), cudaMemcpyDeviceToHost, s);
+        };
+        auto rows_st = [&](int r0, int r1) {
+            return cudaMemcpyAsync(res->stats + (size_t)r0 * P, a.stats + (size_t)r0 * P,
+                                   (size_t)(r1 - r0) * P * sizeof(float), cudaMemcpyDeviceToHost, s);
+        };
+        const bool t_ks = (o.tests & (NCB_TEST_KS | NCB_TEST_AUTO)) != 0, t_mw = (o.tests & NCB_TEST_MW) != 0,
+                   t_tt = (o.tests & NCB_TEST_TT) != 0, t_gmm = (o.tests & (NCB_TEST_GMM | NCB_TEST_AUTO)) != 0,
+                   t_logit = t_gmm && (o.tests & NCB_TEST_LOGIT) != 0;
+        // runs of consecutive requested rows
+        const bool want[NCB_PV_ROWS] = {t_ks, t_ks, t_mw, t_mw, t_tt, t_tt, t_gmm, t_logit, t_logit};
+        for (int r = 0; r < NCB_PV_ROWS;) {
+            if (!want[r]) { ++r; continue; }
+            int e = r;
+            while (e < NCB_PV_ROWS && want[e]) ++e;
+            CK(rows_pv(r, e));
+            r = e;
+        }
+        CK(rows_st(0, t_gmm ? NCB_ST_GMM_LOR + 1 : NCB_ST_GMM_LOR));
+        if (n_vars == 3) CK(rows_st(NCB_ST_C1_MEAN_MOTOR, NCB_ST_ROWS));
+        if (a.counts && t_gmm && o.cluster_counts != NCB_COUNTS_NONE)
+            CK(cudaMemcpyAsync(res->counts, a.counts, b_cnt, cudaMemcpyDeviceToHost, s));
         if (a.diag_i64) CK(cudaMemcpyAsync(res->diag_i64, a.diag_i64, b_di, cudaMemcpyDeviceToHost, s));
         if (a.diag_f64) CK(cudaMemcpyAsync(res->diag_f64, a.diag_f64, b_df, cudaMemcpyDeviceToHost, s));
     }
     return NCB_OK;
 }
 
+int64_t ncb_results_host_bytes(const ncb_handle *h, int64_t P, int32_t n_vars, int with_counts) {
+    if (!h || P < 0) return 0;
+    const ncb_opts &o = h->opts;
+    const bool t_ks = (o.tests & (NCB_TEST_KS | NCB_TEST_AUTO)) != 0, t_mw = (o.tests & NCB_TEST_MW) != 0,
+               t_tt = (o.tests & NCB_TEST_TT) != 0, t_gmm = (o.tests & (NCB_TEST_GMM | NCB_TEST_AUTO)) != 0,
+               t_logit = t_gmm && (o.tests & NCB_TEST_LOGIT) != 0;
+    int64_t per = sizeof(int32_t);
+    per += (int64_t)sizeof(double) * (2 * t_ks + 2 * t_mw + 2 * t_tt + t_gmm + 2 * t_logit);
+    per += (int64_t)sizeof(float) * ((t_gmm ? NCB_ST_GMM_LOR + 1 : NCB_ST_GMM_LOR) + (n_vars == 3 ? 6 : 0));
+    if (with_counts && t_gmm && o.cluster_counts != NCB_COUNTS_NONE) per += (int64_t)o.n_samples * 2 * sizeof(uint32_t);
+    return per * P;
+}
+
 int ncb_wait(ncb_handle *h, void *stream) {
     if (!h) return NCB_ERR_INVALID;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    // the kernels OR NCB_POS_TOO_MANY_READS into the handle's mapped host word; the results of
+    // every other position are in place, the flagged ones hold the NaN / 0 defaults
+    volatile int32_t *flag = h->flag_host;
+    if (flag && *flag) {
+        *flag = 0;
+        return fail(h, NCB_ERR_TOO_MANY_READS,
+                    "a position holds more reads than NCB_MAX_READS or than the batch declared "
+                    "(status NCB_POS_TOO_MANY_READS; its result row holds the defaults)");
+    }
     return NCB_OK;
 }
 
@@ -440,7 +513,7 @@ int ncb_ks_exact_pvalues(ncb_handle *h, int64_t n, const int32_t *n0, const int3
     if (n == 0) return NCB_OK;
     if (!n0 || !n1 || !hstat || !p_out) return fail(h, NCB_ERR_INVALID, "ncb_ks_exact_pvalues: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const void *d0, *d1, *dh;
     int r;
     if ((r = stage_in(h, h->unit_a, n0, (size_t)n * 4, memory, s, &d0)) != NCB_OK) return r;
@@ -471,7 +544,7 @@ int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues,
     if (n == 0) return NCB_OK;
     if (!pvalues || !qvalues) return fail(h, NCB_ERR_INVALID, "ncb_bh_fdr: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     size_t sb = ncb_bh_fdr_scratch_bytes(n);
     ENSURE(h->fdr_scratch, sb);
     const double *dp = pvalues;
@@ -532,7 +605,7 @@ int ncb_context_combine(ncb_handle *h, int64_t n_tx, const int64_t *tx_offsets, 
     }
     const int64_t total = track[n_tx];
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     ENSURE(h->ctx_tx, (size_t)(n_tx + 1) * 8);
     ENSURE(h->ctx_track, (size_t)(n_tx + 1) * 8);
     ENSURE(h->ctx_idx, (size_t)n * 4);
@@ -569,7 +642,8 @@ int ncb_set_timing(ncb_handle *h, int enabled) {
     if (!h) return NCB_ERR_INVALID;
     h->timing = enabled ? 1 : 0;
     if (enabled) {   // start a new log
-        cudaSetDevice(h->device);
+        DeviceGuard guard;
+        guard.enter(h->device);
         cudaDeviceSynchronize();
         for (cudaEvent_t e : h->ev_log) cudaEventDestroy(e);
         h->ev_log.clear();
@@ -581,7 +655,7 @@ int ncb_set_timing(ncb_handle *h, int enabled) {
 int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_stats,
                       double *ms_gmm, double *ms_ks) {
     if (!h) return NCB_ERR_INVALID;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     double a = 0, b = 0, c = 0, d = 0;
     const size_t nb = h->ev_log.size() / 5;
     for (size_t i = 0; i < nb; ++i) {
@@ -605,7 +679,7 @@ int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, do
 int ncb_last_timing(ncb_handle *h, float *ms_position, float *ms_ks, float *ms_total) {
     if (!h) return NCB_ERR_INVALID;
     if (!h->timed) return fail(h, NCB_ERR_INVALID, "ncb_last_timing: the last ncb_compare was not timed");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaEventSynchronize(h->ev[4]));
     float a = 0, b = 0, c = 0;
     CK(cudaEventElapsedTime(&a, h->ev[1], h->ev[3]));
@@ -634,7 +708,7 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, double a, 
 
 int ncb_probe_fp64_peak(ncb_handle *h, double *tflops, void *stream) {
     if (!h || !tflops) return NCB_ERR_INVALID;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
     ENSURE(h->unit_a, 256);
     const int iters = 1 << 13, blocks = h->sm_count * 8, threads = 256;   // ~1 ms per repetition

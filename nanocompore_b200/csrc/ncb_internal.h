@@ -14,6 +14,8 @@ struct NcbDeviceArgs {
     int32_t n_reads;             // dense R
     int32_t n_vars;              // floats per entry (2 for CSR, V for dense)
     int32_t max_entries;         // upper bound on the entries of a position (dense: R), 0 = unknown
+    int32_t signal_i16;          // 1: `signal` holds int16 codes (NCB_LAYOUT_CSR_I16), value = (float)code
+    int32_t *error_flag;         // mapped host word: NCB_POS_TOO_MANY_READS is OR-ed in when a position is rejected
     // options
     int32_t tests;
     int32_t n_samples;
@@ -49,6 +51,7 @@ struct NcbDeviceArgs {
 //   class 4   : one 256-thread CTA per position, 8 entries per thread
 //   class 5   : one 512-thread CTA per position, 8 entries per thread
 //   class 6   : one 1024-thread CTA per position, 10 entries per thread
+#define NCB_TIMING_LOG_MAX 4096   /* batches kept in a handle's timing log */
 enum { NCB_NUM_CLASSES = 7, NCB_NUM_PHASES = 4 };   // phases: statistics / mixture, 2 / 3 variables
 #define NCB_WL_COUNTERS (NCB_NUM_CLASSES * (1 + NCB_NUM_PHASES))
 static const int NCB_CLASS_CAP[NCB_NUM_CLASSES] = {128, 256, 512, 1024, 2048, 4096, NCB_MAX_READS};

@@ -6,6 +6,7 @@
 // the dense tensor altogether.
 #include <math.h>
 #include <string.h>
+#include <atomic>
 #include <exception>
 #include <thread>
 #include <vector>
@@ -37,6 +38,16 @@ void parallel_for(int64_t n, int threads, F f) {
 inline bool covered(const float *row, int V) {
     // a read is kept at a position when intensity or dwell is a number
     return !(row[0] != row[0]) || !(row[1] != row[1]);
+}
+
+// float32 -> int16 code of NCB_LAYOUT_CSR_I16: NaN -> -32768; an integer in [-32767, 32767] -> itself;
+// anything else is not representable (`bad` is raised, the code written is meaningless)
+inline int16_t code_i16(float x, bool &bad) {
+    if (x != x) return (int16_t)-32768;
+    if (!(x >= -32767.0f && x <= 32767.0f)) { bad = true; return 0; }
+    const int16_t c = (int16_t)x;
+    if ((float)c != x) bad = true;
+    return c;
 }
 
 }  // namespace
@@ -79,6 +90,34 @@ int ncb_pack_fill(const float *data, const uint8_t *label, int64_t n_positions, 
         }
     });
     return NCB_OK;
+}
+
+int ncb_pack_fill_i16(const float *data, const uint8_t *label, int64_t n_positions, int32_t n_reads,
+                      int32_t n_vars, const int64_t *pos_offsets, int16_t *signal_out, uint8_t *label_out,
+                      int threads) {
+    if (!data || !label || !pos_offsets || !signal_out || !label_out || n_positions < 0 ||
+        n_reads < 0 || n_vars < 2)
+        return NCB_ERR_INVALID;
+    std::atomic<int> any_bad(0);
+    std::atomic<int> *flag = &any_bad;
+    parallel_for(n_positions, threads, [=](int64_t lo, int64_t hi) {
+        bool bad = false;
+        for (int64_t p = lo; p < hi; ++p) {
+            const float *row = data + p * (int64_t)n_reads * n_vars;
+            int64_t o = pos_offsets[p];
+            for (int r = 0; r < n_reads; ++r) {
+                const float *e = row + (int64_t)r * n_vars;
+                if (covered(e, n_vars)) {
+                    signal_out[2 * o] = code_i16(e[0], bad);
+                    signal_out[2 * o + 1] = code_i16(e[1], bad);
+                    label_out[o] = label[r];
+                    ++o;
+                }
+            }
+        }
+        if (bad) flag->store(1);
+    });
+    return any_bad.load() ? NCB_ERR_INVALID : NCB_OK;
 }
 
 // ---- planar read-major rows -> CSR ---------------------------------------------------------
@@ -156,6 +195,47 @@ int ncb_pack_rows_fill(const float *const *intensity, const float *const *dwell,
         }
     });
     return NCB_OK;
+}
+
+int ncb_pack_rows_fill_i16(const float *const *intensity, const float *const *dwell,
+                           const uint8_t *row_label, int64_t n_rows, int64_t n_positions,
+                           int32_t motor_offset, const int64_t *pos_offsets, int16_t *signal_out,
+                           uint8_t *label_out, int threads) {
+    if (n_rows < 0 || n_positions < 0 || motor_offset < 0 ||
+        (n_positions > 0 && (!pos_offsets || !signal_out || !label_out)) ||
+        (n_rows > 0 && (!intensity || !dwell || !row_label)))
+        return NCB_ERR_INVALID;
+    const int V = motor_offset > 0 ? 3 : 2;
+    const float NaN = nanf("");
+    const int64_t tiles = (n_positions + ROW_TILE - 1) / ROW_TILE;
+    std::atomic<int> any_bad(0);
+    std::atomic<int> *flag = &any_bad;
+    parallel_for(tiles, threads, [=](int64_t t_lo, int64_t t_hi) {
+        bool bad = false;
+        for (int64_t t = t_lo; t < t_hi; ++t) {
+            const int64_t p0 = t * ROW_TILE, p1 = p0 + ROW_TILE < n_positions ? p0 + ROW_TILE : n_positions;
+            int64_t cur[ROW_TILE];
+            for (int64_t i = 0; i < p1 - p0; ++i) cur[i] = pos_offsets[p0 + i];
+            for (int64_t r = 0; r < n_rows; ++r) {
+                const float *x = intensity[r], *y = dwell[r];
+                const uint8_t lab = row_label[r];
+                for (int64_t p = p0; p < p1; ++p) {
+                    const float xv = x[p], yv = y[p];
+                    float mv = NaN;
+                    if (motor_offset > 0 && p + motor_offset < n_positions) mv = y[p + motor_offset];
+                    if (is_num(xv) || is_num(yv) || is_num(mv)) {
+                        const int64_t o = cur[p - p0]++;
+                        signal_out[V * o] = code_i16(xv, bad);
+                        signal_out[V * o + 1] = code_i16(yv, bad);
+                        if (V == 3) signal_out[V * o + 2] = code_i16(mv, bad);
+                        label_out[o] = lab;
+                    }
+                }
+            }
+        }
+        if (bad) flag->store(1);
+    });
+    return any_bad.load() ? NCB_ERR_INVALID : NCB_OK;
 }
 
 }  // extern "C"

@@ -47,8 +47,9 @@ def make_labels(samples, conditions):
 class CsrBatch:
     """Ragged batch: the valid reads of each position, position after position.
 
-    pos_offsets int64 [P+1]; signal float32 [E, V] {intensity, dwell[, motor dwell]}, V = 2 or 3;
-    label uint8 [E].
+    pos_offsets int64 [P+1]; signal [E, V] {intensity, dwell[, motor dwell]}, V = 2 or 3 -- float32
+    (NCB_LAYOUT_CSR) or int16 codes (NCB_LAYOUT_CSR_I16: value = float(code), -32768 = NaN, the encoding
+    of Uncalled4's tags, 5 instead of 9 bytes per entry on the host-to-device link); label uint8 [E].
     Tensors are either all pinned-host or all on the device."""
     pos_offsets: torch.Tensor
     signal: torch.Tensor
@@ -67,6 +68,18 @@ class CsrBatch:
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.pos_offsets, self.signal, self.label))
 
+    @property
+    def wire(self):
+        return 'i16' if self.signal.dtype == torch.int16 else 'f32'
+
+    def signal_f32(self):
+        """The entries as float32 numbers whatever the wire format (int16 code -32768 = NaN)."""
+        if self.signal.dtype != torch.int16:
+            return self.signal
+        out = self.signal.to(torch.float32)
+        out[self.signal == -32768] = float('nan')
+        return out
+
     def to(self, device, non_blocking=False):
         return CsrBatch(self.pos_offsets.to(device, non_blocking=non_blocking),
                         self.signal.to(device, non_blocking=non_blocking),
@@ -77,9 +90,13 @@ class CsrBatch:
                         self.max_entries)
 
 
-def pack_csr(transcripts, pin=False, threads=None):
+def pack_csr(transcripts, pin=False, threads=None, wire='f32'):
     """Packs dense reference tensors into one CSR batch with libncb's host packer
     (ncb_pack_count / ncb_pack_fill, multi-threaded C++).
+
+    ``wire``: 'f32' -> float32 entries; 'i16' -> int16 entries (every number of the tensors must be an
+    integer in [-32767, 32767], as in Uncalled4 input: ValueError otherwise); 'auto' -> int16 when
+    the data allows it, else float32.
 
     ``transcripts``: iterable of (data (P,R,V>=2) float32 with NaN, samples (R,), conditions (R,)).
     A read is kept at a position when any of its two variables is a number.  Read order inside
@@ -113,19 +130,32 @@ def pack_csr(transcripts, pin=False, threads=None):
     if pin:
         t_off = t_off.pin_memory()
         offsets = t_off.numpy()
-    t_sig = torch.empty((E, 2), dtype=torch.float32, **kw)
+    if wire not in ('f32', 'i16', 'auto'):
+        raise ValueError(f"wire must be 'f32', 'i16' or 'auto', not {wire!r}")
     t_lab = torch.empty((E,), dtype=torch.uint8, **kw)
-    p0 = 0
-    ptx, pidx = [], []
-    for ti, (data, lab) in enumerate(items):
-        P = data.shape[0]
-        rc = lib.ncb_pack_fill(data.ctypes.data, lab.ctypes.data, P, data.shape[1], data.shape[2],
-                               offsets[p0:].ctypes.data, t_sig.data_ptr(), t_lab.data_ptr(), threads)
-        if rc != L.NCB_OK:
-            raise L.NcbError(rc, "ncb_pack_fill")
-        ptx.append(np.full(P, ti, dtype=np.int32))
-        pidx.append(np.arange(P, dtype=np.int32))
-        p0 += P
+    ptx = [np.full(d.shape[0], ti, dtype=np.int32) for ti, (d, _) in enumerate(items)]
+    pidx = [np.arange(d.shape[0], dtype=np.int32) for d, _ in items]
+
+    def fill(i16):
+        t_sig = torch.empty((E, 2), dtype=torch.int16 if i16 else torch.float32, **kw)
+        fn = lib.ncb_pack_fill_i16 if i16 else lib.ncb_pack_fill
+        p0 = 0
+        for data, lab in items:
+            P = data.shape[0]
+            rc = fn(data.ctypes.data, lab.ctypes.data, P, data.shape[1], data.shape[2],
+                    offsets[p0:].ctypes.data, t_sig.data_ptr(), t_lab.data_ptr(), threads)
+            if rc != L.NCB_OK:
+                if i16 and rc == L.NCB_ERR_INVALID:
+                    return None      # a value is not an int16 code
+                raise L.NcbError(rc, fn.__name__)
+            p0 += P
+        return t_sig
+
+    t_sig = fill(True) if wire in ('i16', 'auto') else None
+    if t_sig is None:
+        if wire == 'i16':
+            raise ValueError("pack_csr(wire='i16'): the data holds values that are not int16 codes")
+        t_sig = fill(False)
     batch = CsrBatch(t_off, t_sig, t_lab, int(all_counts.max()) if all_counts.size else 0)
     return (batch,
             np.concatenate(ptx) if ptx else np.zeros(0, np.int32),
@@ -160,9 +190,17 @@ class Results:
         kw = dict(device=device) if on_dev else dict(pin_memory=pinned)
         self.memory = L.NCB_MEM_DEVICE if on_dev else L.NCB_MEM_HOST
         self.status = torch.empty(P, dtype=torch.int32, **kw)
-        self.pvalues = torch.empty((L.NCB_PV_ROWS, P), dtype=torch.float64, **kw)
-        self.stats = torch.empty((L.NCB_ST_ROWS, P), dtype=torch.float32, **kw)
-        self.counts = torch.empty((max(S, 1), 2, P), dtype=torch.int32, **kw)
+        if on_dev:
+            # the kernels write every row of device results
+            self.pvalues = torch.empty((L.NCB_PV_ROWS, P), dtype=torch.float64, **kw)
+            self.stats = torch.empty((L.NCB_ST_ROWS, P), dtype=torch.float32, **kw)
+            self.counts = torch.empty((max(S, 1), 2, P), dtype=torch.int32, **kw)
+        else:
+            # host results receive only the rows of the configured tests (ncb.h, ncb_results): the
+            # others read as "not tested"
+            self.pvalues = torch.full((L.NCB_PV_ROWS, P), float('nan'), dtype=torch.float64, **kw)
+            self.stats = torch.full((L.NCB_ST_ROWS, P), float('nan'), dtype=torch.float32, **kw)
+            self.counts = torch.zeros((max(S, 1), 2, P), dtype=torch.int32, **kw)
         self.diag_i64 = torch.empty((L.NCB_DI_ROWS, P), dtype=torch.int64, **kw) if diagnostics else None
         self.diag_f64 = torch.empty((L.NCB_DF_ROWS, P), dtype=torch.float64, **kw) if diagnostics else None
 
@@ -286,8 +324,10 @@ class Engine:
         b.memory = L.NCB_MEM_DEVICE if on_dev else L.NCB_MEM_HOST
         b.n_positions = P
         b.n_entries = batch.n_entries
-        assert batch.pos_offsets.dtype == torch.int64 and batch.signal.dtype == torch.float32
-        assert batch.label.dtype == torch.uint8
+        assert batch.pos_offsets.dtype == torch.int64 and batch.label.dtype == torch.uint8
+        assert batch.signal.dtype in (torch.float32, torch.int16)
+        if batch.signal.dtype == torch.int16:
+            b.layout = L.NCB_LAYOUT_CSR_I16
         assert batch.signal.is_contiguous() and batch.label.is_contiguous()
         b.pos_offsets = batch.pos_offsets.data_ptr()
         b.signal = batch.signal.data_ptr()
@@ -334,6 +374,10 @@ class Engine:
 
     def wait(self, stream=None):
         self._check(self.lib.ncb_wait(self._handle, self._stream(stream)))
+
+    def results_host_bytes(self, n_positions, n_vars=2, with_counts=True):
+        """Bytes one ``compare_*`` call with host results copies device -> host."""
+        return int(self.lib.ncb_results_host_bytes(self._handle, n_positions, n_vars, int(with_counts)))
 
     # ------------------------------------------------------------------ unit entry points
     def ks_exact_pvalues(self, n0, n1, h):

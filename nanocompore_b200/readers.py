@@ -115,8 +115,9 @@ class TranscriptRows:
 
     def __init__(self, n_positions, intensity, dwell, sample_ids, condition_ids, read_names=None):
         self.n_positions = int(n_positions)
-        self.intensity = np.ascontiguousarray(intensity, dtype=np.float32).reshape(-1, self.n_positions)
-        self.dwell = np.ascontiguousarray(dwell, dtype=np.float32).reshape(-1, self.n_positions)
+        n_rows = len(sample_ids)     # (R, 0) is a legal shape: no rows / no positions are empty sets
+        self.intensity = np.ascontiguousarray(intensity, dtype=np.float32).reshape(n_rows, self.n_positions)
+        self.dwell = np.ascontiguousarray(dwell, dtype=np.float32).reshape(n_rows, self.n_positions)
         assert self.intensity.shape == self.dwell.shape
         self.sample_ids = np.asarray(sample_ids, dtype=np.int64)
         self.condition_ids = np.asarray(condition_ids, dtype=np.int64)
@@ -218,6 +219,7 @@ class Uncalled4Reader:
 
     # several transcripts may be read at once: the native handles are read-only after the index is built
     concurrent_reads = True
+    int16_source = True       # tag values are int16: the pipeline packs NCB_LAYOUT_CSR_I16 entries
 
     def __init__(self, config, threads=None):
         self._conf = config
@@ -340,8 +342,11 @@ def select_reads(rows, max_reads, min_coverage, motor_dwell_offset=0):
     keep = (cov0 >= min_coverage) & (cov1 >= min_coverage) & ((cov0 + cov1) > 0)
     complete = ~np.isnan(rows.intensity) & ~np.isnan(rows.dwell)
     if motor_dwell_offset > 0:
+        # run.py:575-584: with the offset beyond the transcript's end the motor column is all NaN
         motor = np.zeros_like(complete)
-        motor[:, :rows.n_positions - motor_dwell_offset] = ~np.isnan(rows.dwell[:, motor_dwell_offset:])
+        end = rows.n_positions - motor_dwell_offset
+        if end > 0:
+            motor[:, :end] = ~np.isnan(rows.dwell[:, motor_dwell_offset:])
         complete &= motor
     score = complete[:, keep].sum(1)
     order = np.argsort(-score, kind='stable')
@@ -352,10 +357,12 @@ def select_reads(rows, max_reads, min_coverage, motor_dwell_offset=0):
     return rows.take(selected), keep
 
 
-def pack_rows(row_sets, motor_dwell_offset=0, pin=False, threads=None):
+def pack_rows(row_sets, motor_dwell_offset=0, pin=False, threads=None, wire='f32'):
     """Rows of one or more transcripts -> one CSR batch (pos_offsets, signal [E, V], label) with
     V = 3 when ``motor_dwell_offset`` > 0.  Returns (CsrBatch, pos_transcript, pos_index) like
-    ``engine.pack_csr``.  Transcripts are packed concurrently (the native calls release the GIL)."""
+    ``engine.pack_csr``.  Transcripts are packed concurrently (the native calls release the GIL).
+    ``wire`` as in ``engine.pack_csr``: 'i16' / 'auto' write int16 entries (NCB_LAYOUT_CSR_I16) when
+    every value is an int16 code, which Uncalled4 rows are (uncalled4.py:118-192)."""
     lib = L.load()
     threads = threads or _threads()
     V = 3 if motor_dwell_offset > 0 else 2
@@ -382,20 +389,34 @@ def pack_rows(row_sets, motor_dwell_offset=0, pin=False, threads=None):
         if pin:
             t_off = t_off.pin_memory()
             offsets = t_off.numpy()
-        t_sig = torch.empty((E, V), dtype=torch.float32, **kw)
+        if wire not in ('f32', 'i16', 'auto'):
+            raise ValueError(f"wire must be 'f32', 'i16' or 'auto', not {wire!r}")
         t_lab = torch.empty((E,), dtype=torch.uint8, **kw)
         starts = np.concatenate([[0], np.cumsum([r.n_positions for r in row_sets])]).astype(np.int64)
 
-        def fill(k):
-            r = row_sets[k]
-            rc = lib.ncb_pack_rows_fill(ptrs[k][0].ctypes.data, ptrs[k][1].ctypes.data,
-                                        labs[k].ctypes.data, r.n_reads, r.n_positions,
-                                        motor_dwell_offset, offsets[starts[k]:].ctypes.data,
-                                        t_sig.data_ptr(), t_lab.data_ptr(), 1)
-            if rc != L.NCB_OK:
-                raise L.NcbError(rc, "ncb_pack_rows_fill")
+        def fill_all(i16):
+            t_sig = torch.empty((E, V), dtype=torch.int16 if i16 else torch.float32, **kw)
+            fn = lib.ncb_pack_rows_fill_i16 if i16 else lib.ncb_pack_rows_fill
 
-        list(ex.map(fill, range(len(row_sets))))
+            def fill(k):
+                r = row_sets[k]
+                return fn(ptrs[k][0].ctypes.data, ptrs[k][1].ctypes.data,
+                          labs[k].ctypes.data, r.n_reads, r.n_positions,
+                          motor_dwell_offset, offsets[starts[k]:].ctypes.data,
+                          t_sig.data_ptr(), t_lab.data_ptr(), 1)
+
+            for rc in ex.map(fill, range(len(row_sets))):
+                if rc != L.NCB_OK:
+                    if i16 and rc == L.NCB_ERR_INVALID:
+                        return None          # a value is not an int16 code
+                    raise L.NcbError(rc, fn.__name__)
+            return t_sig
+
+        t_sig = fill_all(True) if wire in ('i16', 'auto') else None
+        if t_sig is None:
+            if wire == 'i16':
+                raise ValueError("pack_rows(wire='i16'): the rows hold values that are not int16 codes")
+            t_sig = fill_all(False)
     ptx = np.concatenate([np.full(r.n_positions, k, dtype=np.int32) for k, r in enumerate(row_sets)]) \
         if row_sets else np.zeros(0, np.int32)
     pidx = np.concatenate([np.arange(r.n_positions, dtype=np.int32) for r in row_sets]) \
@@ -461,7 +482,9 @@ class TranscriptPipeline:
             live.append(i)
             row_sets.append(rows)
             masks.append(keep)
-        packed = pack_rows(row_sets, offset, pin=True) if live else None
+        # Uncalled4 rows are int16 tag values: they travel as 5-byte entries; anything else as float32
+        wire = 'auto' if getattr(self._reader, 'int16_source', False) else 'f32'
+        packed = pack_rows(row_sets, offset, pin=True, wire=wire) if live else None
         return transcripts, live, row_sets, masks, packed
 
     def finish(self, prepared):
@@ -477,7 +500,9 @@ class TranscriptPipeline:
         # both conditions (run.py:511-515): the statistics kernel applies both (min_coverage >= 1);
         # after a downsample the reference keeps the positions chosen BEFORE it, so the host mask
         # decides there and the kernel's filter is off
-        pre_filtered = any(m is not None for m in masks)
+        # min_coverage 0 keeps every position with a valid intensity in EITHER condition (run.py:587):
+        # the kernel's per-condition filter cannot express that, so the host mask decides there too
+        pre_filtered = any(m is not None for m in masks) or min_cov == 0
         res = self._comparator.compare_packed(batch, self._device,
                                               min_coverage=0 if pre_filtered else max(min_cov, 1))
         klen, _ = kit_geometry(conf.get_kit())

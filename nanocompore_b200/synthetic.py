@@ -28,9 +28,14 @@ class SyntheticTranscript:
     modified: np.ndarray      # (P,) bool -- ground truth, not used by the tests
 
 
-def make_transcript(rng, n_positions, reads_per_cond, *, quantised=False,
+def make_transcript(rng, n_positions, reads_per_cond, *, quantised=False, uncalled4=False,
                     mod_fraction=0.10, gap_rate=0.02, span_start_max=0.3,
                     name='tx', n_replicates=2):
+    """``uncalled4``: the values are what the Uncalled4 reader hands over (uncalled4.py:118-192, the
+    int16 tags ``uc`` / ``ul`` copied into the float32 tensor): the current as an integer code,
+    250 codes per pA around 95 pA (the fixture BAMs hold codes of -14 000 .. 18 000 with a
+    per-position spread of ~1 000), the dwell as a whole number of samples at 4 kHz (>= 1).  The same
+    draws as the default generator, so a position has the same shape in both."""
     P, n = int(n_positions), int(reads_per_cond)
     R = 2 * n
     S = 2 * n_replicates
@@ -53,7 +58,10 @@ def make_transcript(rng, n_positions, reads_per_cond, *, quantised=False,
     inten = np.where(hit, inten + f32(3.0) * sigma[:, None], inten)
     dwell = np.where(hit, dwell * f32(1.6), dwell)
 
-    if quantised:
+    if uncalled4:
+        inten = np.clip(np.round((inten - f32(95.0)) * f32(250.0)), f32(-32767.0), f32(32767.0))
+        dwell = np.clip(np.round(dwell * f32(4000.0)), f32(1.0), f32(32767.0))
+    elif quantised:
         # mimics Uncalled4 int16 current levels / integer sample counts: true ties
         inten = np.round(inten * f32(64.0)) / f32(64.0)
         dwell = np.maximum(np.round(dwell * f32(4000.0)), f32(1.0)) / f32(4000.0)

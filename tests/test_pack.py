@@ -62,3 +62,37 @@ def test_pack_csr_rejects_mismatched_ids():
         pack_csr([(data, np.zeros(4, dtype=np.int64), np.zeros(4, dtype=np.int64))])
     with pytest.raises(ValueError):
         pack_csr([(data, np.zeros(5, dtype=np.int64), np.zeros(4, dtype=np.int64))])
+
+
+def test_int16_wire_is_lossless_on_uncalled4_like_data():
+    """NCB_LAYOUT_CSR_I16: Uncalled4 hands over int16 tag values (uncalled4.py:118-192); packed as
+    int16 codes they decode to the float32 entries bit for bit, NaN included."""
+    rng = np.random.default_rng(5)
+    txs = []
+    for P, n in ((60, 25), (31, 40)):
+        tx = make_transcript(rng, P, n, uncalled4=True)
+        tx.data[3, :, 0] = np.nan              # intensity missing, dwell present: entries are kept
+        txs.append((tx.data, tx.samples, tx.conditions))
+    f32, _, _ = pack_csr(txs)
+    i16, _, _ = pack_csr(txs, wire='i16', threads=3)
+    auto, _, _ = pack_csr(txs, wire='auto')
+    assert f32.wire == 'f32' and i16.wire == 'i16' and auto.wire == 'i16'
+    assert i16.signal.dtype.itemsize == 2 and i16.nbytes() < 0.6 * f32.nbytes()
+    assert np.array_equal(i16.pos_offsets.numpy(), f32.pos_offsets.numpy())
+    assert np.array_equal(i16.label.numpy(), f32.label.numpy())
+    assert np.array_equal(i16.signal_f32().numpy(), f32.signal.numpy(), equal_nan=True)
+    assert np.array_equal(auto.signal.numpy(), i16.signal.numpy())
+    assert (i16.signal.numpy()[np.isnan(f32.signal.numpy())] == -32768).all()
+
+
+@pytest.mark.parametrize('bad', [0.5, 40000.0, -32768.0, np.inf])
+def test_int16_wire_refuses_values_that_are_not_codes(bad):
+    rng = np.random.default_rng(6)
+    tx = make_transcript(rng, 20, 10, uncalled4=True)
+    tx.data[7, 4, 1] = bad
+    item = [(tx.data, tx.samples, tx.conditions)]
+    with pytest.raises(ValueError, match='int16'):
+        pack_csr(item, wire='i16')
+    auto, _, _ = pack_csr(item, wire='auto')           # falls back to float32 entries
+    f32, _, _ = pack_csr(item)
+    assert auto.wire == 'f32' and np.array_equal(auto.signal.numpy(), f32.signal.numpy(), equal_nan=True)

@@ -15,7 +15,8 @@ from nanocompore_b200.engine import pack_csr_numpy
 @pytest.fixture
 def unpinned(monkeypatch):
     pack_rows = R.pack_rows       # pinned memory needs a CUDA context
-    monkeypatch.setattr(R, 'pack_rows', lambda rows, offset=0, pin=False, threads=None: pack_rows(rows, offset))
+    monkeypatch.setattr(R, 'pack_rows',
+                        lambda rows, offset=0, pin=False, threads=None, wire='f32': pack_rows(rows, offset, wire=wire))
 
 
 class Comparator:
@@ -40,7 +41,9 @@ def test_prepare_packs_what_the_reader_returns(tmp_path, unpinned, kind):
     off, sig, lab = pack_csr_numpy([(r.dense(), r.sample_ids, r.condition_ids) for r in row_sets])
     assert np.array_equal(batch.pos_offsets.numpy(), off)
     assert np.array_equal(batch.label.numpy(), lab)
-    assert np.array_equal(batch.signal.numpy(), sig, equal_nan=True)
+    # Uncalled4 rows are int16 tag values and travel as int16 entries; SQLite blobs as float32
+    assert batch.wire == ('i16' if kind == 'bam' else 'f32')
+    assert np.array_equal(batch.signal_f32().numpy(), sig, equal_nan=True)
     reader.close()
 
 
@@ -61,7 +64,7 @@ def test_prepare_downsample_and_motor(tmp_path, unpinned):
     # third column = the dwell 4 positions downstream of the same read (run.py:577-584)
     r = row_sets[0]
     off = batch.pos_offsets.numpy()
-    sig = batch.signal.numpy()
+    sig = batch.signal_f32().numpy()
     p = 10
     # a read is kept at a position when any of its three variables is a number (include/ncb.h)
     rows_at_p = np.nonzero(~(np.isnan(r.intensity[:, p]) & np.isnan(r.dwell[:, p]) & np.isnan(r.dwell[:, p + 4])))[0]

@@ -404,7 +404,8 @@ def test_pipeline_skips_a_transcript_whose_files_do_not_parse(tmp_path, monkeypa
 
     messages = []
     pack_rows = R.pack_rows
-    monkeypatch.setattr(R, 'pack_rows', lambda rows, offset=0, pin=False, threads=None: pack_rows(rows, offset))
+    monkeypatch.setattr(R, 'pack_rows',
+                        lambda rows, offset=0, pin=False, threads=None, wire='f32': pack_rows(rows, offset, wire=wire))
     pipe = R.TranscriptPipeline(cfg, R.Uncalled4Reader(cfg), comparator=None,
                                 log=lambda level, msg: messages.append((level, msg)))
     transcripts, live, row_sets, masks, packed = pipe.prepare([T(n, l) for n, l in refs])
