@@ -204,6 +204,27 @@ class Results:
         self.diag_i64 = torch.empty((L.NCB_DI_ROWS, P), dtype=torch.int64, **kw) if diagnostics else None
         self.diag_f64 = torch.empty((L.NCB_DF_ROWS, P), dtype=torch.float64, **kw) if diagnostics else None
 
+    def carve(self, n_positions):
+        """Result buffers of exactly ``n_positions`` <= P positions carved from this object's memory
+        (libncb writes rows of length P back to back, so a smaller batch needs arrays of its own
+        shape): pinned buffers allocated once for the largest batch serve batches of any size.  Rows
+        the configured tests do not write hold whatever the memory held before."""
+        n = int(n_positions)
+        if n == self.n_positions:
+            return self
+        if n > self.n_positions:
+            raise ValueError(f"carve({n}) from result buffers of {self.n_positions} positions")
+        v = Results.__new__(Results)
+        v.n_positions, v.n_samples, v.memory = n, self.n_samples, self.memory
+        v.status = self.status[:n]
+        v.pvalues = self.pvalues.view(-1)[:L.NCB_PV_ROWS * n].view(L.NCB_PV_ROWS, n)
+        v.stats = self.stats.view(-1)[:L.NCB_ST_ROWS * n].view(L.NCB_ST_ROWS, n)
+        s = self.counts.shape[0]
+        v.counts = self.counts.view(-1)[:s * 2 * n].view(s, 2, n)
+        v.diag_i64 = None if self.diag_i64 is None else self.diag_i64.view(-1)[:L.NCB_DI_ROWS * n].view(L.NCB_DI_ROWS, n)
+        v.diag_f64 = None if self.diag_f64 is None else self.diag_f64.view(-1)[:L.NCB_DF_ROWS * n].view(L.NCB_DF_ROWS, n)
+        return v
+
     def struct(self):
         r = L.NcbResults()
         r.memory = self.memory

@@ -21,10 +21,22 @@ import sys
 import types
 
 REFERENCE_ROOT = '/root/reference'
+# the byte-for-byte copy baseline/stage_reference.py makes for the reference arm of bench.py (git-ignored;
+# it travels to the GPU box, where /root/reference does not exist)
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+
+
+def reference_root():
+    """Where the unmodified reference package can be imported from: /root/reference in the build
+    container, else the staged copy; None when neither is there."""
+    for root in (REFERENCE_ROOT, STAGED_ROOT):
+        if os.path.isfile(os.path.join(root, 'nanocompore', 'comparisons.py')):
+            return root
+    return None
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'nanocompore'))
+    return reference_root() is not None
 
 
 class _Schema:
@@ -67,11 +79,13 @@ def _install_stubs():
 
 def load_reference():
     """Returns the reference's ``nanocompore`` package (comparisons, run, config ...)."""
-    if not reference_available():
-        raise RuntimeError("/root/reference is not present on this machine")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("neither /root/reference nor the staged copy baseline/_ref is present "
+                           "(python baseline/stage_reference.py makes the copy in the build container)")
     _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     pkg = importlib.import_module('nanocompore')
     for sub in ('common', 'config', 'transcript', 'comparisons'):
         importlib.import_module(f'nanocompore.{sub}')

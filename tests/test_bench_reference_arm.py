@@ -1,5 +1,6 @@
 """
-The reference arm of bench.py (`--impl reference`: the CPU port on all host cores) on the CPU:
+The reference arm of bench.py (`--impl reference`: the reference's own code -- /root/reference or the
+staged copy baseline/_ref -- on all host cores, the numpy port as a second field) on the CPU:
 rank 0 prints ONE JSON line with the contract's keys, every other rank exits 0 without work.
 """
 import json
@@ -32,7 +33,11 @@ def test_rank0_prints_the_contract_line():
     assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['n_gpus'] == 2
     assert d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 0 and d['gpu_launches'] == 0
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] == (os.cpu_count() or 1) and cb['value'] == d['value'] and cb['sample']
+    from oracle import refharness
+    kind = 'reference' if refharness.reference_available() else 'port'
+    assert cb['kind'] == kind and cb['cores'] == (os.cpu_count() or 1) and cb['value'] == d['value'] and cb['sample']
+    if kind == 'reference':
+        assert d['port']['kind'] == 'port' and d['port']['value'] > 0
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['config']['workload'].startswith('config3')
 
@@ -46,6 +51,6 @@ def test_product_arm_fails_loudly_without_a_gpu():
         pytest.skip("a GPU is present")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '0',
-                        '--tx-per-step', '1', '--no-cpu-baseline'], env=env, capture_output=True, text=True, timeout=300)
+                        '--tx-per-batch', '1', '--no-cpu-baseline'], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith('{')]

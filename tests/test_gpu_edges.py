@@ -129,8 +129,13 @@ def test_declared_max_entries_skips_classes_but_not_results(engine_factory):
     for key in ('status', 'pvalues', 'stats', 'counts'):
         a, b = got[key].ravel(), want[key].ravel()
         assert ((a == b) | (np.isnan(a.astype(np.float64)) & np.isnan(b.astype(np.float64)))).all(), key
-    dev.max_entries = 100                                                      # too low
-    res = eng.compare_csr(dev).numpy()
+    dev.max_entries = 100                                                      # too low: the wait reports it,
+    from nanocompore_b200.engine import Results                                #   the other rows are complete
+    out = Results(dev.n_positions, 4, dev.signal.device)
+    with pytest.raises(L.NcbError) as err:
+        eng.compare_csr(dev, out)
+    assert err.value.code == L.NCB_ERR_TOO_MANY_READS
+    res = out.numpy()
     over = counts > 100
     assert over.any() and ((res['status'][over] & L.NCB_POS_TOO_MANY_READS) != 0).all()
     assert ((res['status'][~over] & L.NCB_POS_TOO_MANY_READS) == 0).all()

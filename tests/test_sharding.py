@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from nanocompore_b200.sharding import gather_columns, lpt_partition, work_estimate
+from nanocompore_b200.sharding import (fdr_columns, gather_columns, lpt_imbalance, lpt_partition, warm_up,
+                                       work_estimate)
 
 
 def test_lpt_partition_is_deterministic_and_balanced():
@@ -83,3 +84,53 @@ def test_gather_columns_gloo_world2(tmp_path):
     nan = np.isnan(c0)
     assert nan.sum() == 1
     assert (c0[~nan] == keys[~nan] * 0.5).all()
+
+
+def _columns_of(rank, n_cols):
+    rng = np.random.default_rng(100 + rank)
+    n = 37 + 11 * rank                      # ranks hold different numbers of rows
+    cols = rng.random((n_cols, n)) ** 3
+    cols[rng.random((n_cols, n)) < 0.1] = np.nan
+    if n_cols:
+        cols[0, :5] = cols[0, 5:10]         # ties
+    return cols
+
+
+def _fdr_worker(rank, world, port, out, n_cols):
+    from oracle.fdr import fdr_bh
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    bh = lambda p: torch.from_numpy(fdr_bh(p.numpy()))      # noqa: E731  (the GPU tests use Engine.bh_fdr)
+    warm_up(torch.device('cpu'), bh)
+    q = fdr_columns(torch.from_numpy(_columns_of(rank, n_cols)), bh)
+    torch.save(q, f'{out}.{rank}')
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_cols', [1, 3, 5])
+def test_fdr_columns_gloo_world2_equals_the_correction_of_the_whole_table(tmp_path, n_cols):
+    """postprocessing.py:255-285 corrects a column over ALL result rows: sharded over two ranks the
+    q-values must be those of the concatenated column (oracle/fdr.py), whoever owns the column."""
+    from oracle.fdr import fdr_bh
+    out = str(tmp_path / 'q.pt')
+    mp.spawn(_fdr_worker, args=(2, _free_port(), out, n_cols), nprocs=2, join=True)
+    whole = np.concatenate([_columns_of(0, n_cols), _columns_of(1, n_cols)], axis=1)
+    want = np.stack([fdr_bh(whole[c]) for c in range(n_cols)])
+    got = np.concatenate([torch.load(f'{out}.{r}').numpy() for r in range(2)], axis=1)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(got, want, rtol=1e-13, atol=0, equal_nan=True)
+
+
+def test_fdr_columns_single_process():
+    from oracle.fdr import fdr_bh
+    cols = _columns_of(0, 3)
+    q = fdr_columns(torch.from_numpy(cols), lambda p: torch.from_numpy(fdr_bh(p.numpy())))
+    assert np.allclose(q.numpy(), np.stack([fdr_bh(c) for c in cols]), equal_nan=True)
+
+
+def test_lpt_imbalance():
+    w = np.array([4.0, 3.0, 2.0, 1.0])
+    shards = lpt_partition(w, 2)
+    assert lpt_imbalance(w, shards) == 1.0
+    assert lpt_imbalance(w, [np.array([0, 1]), np.array([2, 3])]) == pytest.approx(1.4)
