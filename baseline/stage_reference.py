@@ -25,6 +25,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = '/root/reference/nanocompore'
 DST = os.path.join(HERE, '_ref', 'nanocompore')
+# the reference's own tests of the path (run against this repo's TranscriptComparator by
+# tests/test_reference_tests_gpu.py) and the fixtures its Worker test reads
+TESTS_SRC = '/root/reference/tests'
+TESTS_DST = os.path.join(HERE, '_ref', 'tests')
+TEST_FILES = ['common.py', 'test_comparisons.py', 'test_run.py', 'test_postprocessing.py']
+FIXTURES = ['kd1.bam', 'kd2.bam', 'wt1.bam', 'wt2.bam', 'kd1.bam.bai', 'kd2.bam.bai', 'wt1.bam.bai', 'wt2.bam.bai',
+            'test_reference.fa', 'test_reference.fa.fai']
 
 
 def sha256(path):
@@ -50,8 +57,19 @@ def stage(src=SRC, dst=DST):
             manifest[os.path.relpath(p, dst)] = sha256(p)
     for rel, digest in manifest.items():
         assert sha256(os.path.join(src, rel)) == digest, rel
+    tests = {}
+    if os.path.isdir(TESTS_SRC):
+        if os.path.isdir(TESTS_DST):
+            shutil.rmtree(TESTS_DST)
+        os.makedirs(os.path.join(TESTS_DST, 'fixtures'))
+        for name in TEST_FILES + [os.path.join('fixtures', f) for f in FIXTURES]:
+            a, b = os.path.join(TESTS_SRC, name), os.path.join(TESTS_DST, name)
+            if os.path.isfile(a):
+                shutil.copyfile(a, b)
+                tests[name] = sha256(b)
     with open(os.path.join(os.path.dirname(dst), 'MANIFEST.json'), 'w') as f:
-        json.dump({'source': src, 'version': '2.0.0', 'files': manifest}, f, indent=1, sort_keys=True)
+        json.dump({'source': src, 'version': '2.0.0', 'files': manifest, 'tests': tests}, f, indent=1,
+                  sort_keys=True)
     return dst
 
 

@@ -101,12 +101,24 @@ typedef struct {
     int32_t min_coverage;       /* per condition, on valid intensities (run.py:511-515); 0 = off */
     int32_t dwell_is_raw;       /* 1: apply log10(dwell + 1e-10) (run.py:573); 0: already done */
     int32_t cluster_counts;     /* NCB_COUNTS_*                                          */
-    int32_t em_fp64;            /* reserved, must be 1: EM runs in fp64 on the float32
-                                   standardised values (the definition in oracle/gmm.py) */
+    int32_t em_fp64;            /* 1 (default): EM runs in fp64 on the float32 standardised values -- the
+                                   definition in oracle/gmm.py, bit-exact counts.  0: the per-read E-step
+                                   (densities, responsibilities, log-likelihood terms) runs in float32 like
+                                   the reference's fit (dtype=torch.float32, comparisons.py:33, 345), the
+                                   sufficient statistics are still accumulated in fp64 and the M-step is
+                                   fp64: faster, and within float32 rounding of the definition -- a read
+                                   whose two densities are within ~1e-6 of each other, or a stop test
+                                   within ~1e-7 of em_tol, can fall the other way (mixture
+                                   kernel: measured flip rate)                                          */
     int32_t em_max_iter;        /* 100                                                   */
     int32_t diagnostics;        /* 1: fill ncb_results.diag_* (integer statistics, GMM parameters) */
     double em_tol;              /* 1e-3                                                  */
     double reg_covar;           /* 1e-6                                                  */
+    int32_t input_standardised; /* 1: the values are already filtered and standardised (what
+                                   compare_transcript hands to _nonparametric_test / _gmm_test_split,
+                                   comparisons.py:95-120, 218, 338): no outlier rule, no scaling, no
+                                   bad-std drop; the shift statistics are those of the values given */
+    int32_t reserved;           /* 0                                                      */
 } ncb_opts;
 
 /* label byte of a read: bit 0 = condition id (0/1), bits 1..7 = sample id */

@@ -63,7 +63,8 @@ class NcbOpts(C.Structure):
                 ('depleted_condition', C.c_int32), ('min_coverage', C.c_int32),
                 ('dwell_is_raw', C.c_int32), ('cluster_counts', C.c_int32), ('em_fp64', C.c_int32),
                 ('em_max_iter', C.c_int32), ('diagnostics', C.c_int32),
-                ('em_tol', C.c_double), ('reg_covar', C.c_double)]
+                ('em_tol', C.c_double), ('reg_covar', C.c_double),
+                ('input_standardised', C.c_int32), ('reserved', C.c_int32)]
 
 
 class NcbBatch(C.Structure):

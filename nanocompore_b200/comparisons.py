@@ -76,12 +76,16 @@ class TranscriptComparator:
     def _engine(self, device):
         """One libncb handle per CUDA device, created on first use (no CUDA work at import or
         construction time, so fork and spawn start methods both work: run.py:364-372)."""
-        if isinstance(device, str) and device.startswith('cuda'):
-            dev = torch.device(device)
-            index = dev.index if dev.index is not None else 0
-        else:
-            # the reference's 'cpu' device string: this implementation has no CPU path
-            index = 0
+        if isinstance(device, torch.device):
+            device = str(device)
+        if not (isinstance(device, str) and device.startswith('cuda')):
+            # the reference's default is `devices: {'cpu': 2}` (config.py:196-214): there is no CPU
+            # path here, and running such a worker silently on GPU 0 would oversubscribe it
+            raise NanocomporeError(
+                f"device {device!r}: nanocompore_b200 runs the comparison on CUDA devices only; "
+                "set `devices: {'cuda:0': <workers>, ...}` in the configuration")
+        dev = torch.device(device)
+        index = dev.index if dev.index is not None else 0
         if index not in self._engines:
             methods = [m for m in self._config.get_comparison_methods()]
             for m in methods:
@@ -126,6 +130,135 @@ class TranscriptComparator:
         res = engine.compare_dense(dev_data, labels).numpy()
         return transcript, self._assemble(transcript, positions, res['status'], res['pvalues'],
                                           res['stats'], res['counts'], with_motor)
+
+    # ------------------------------------------------------------------ the reference's stages
+    # compare_transcript above runs every stage in one libncb call.  The methods below are the
+    # stages under the names the reference gives them (its own tests call them directly:
+    # tests/test_comparisons.py:21-154, 307-504); each is one libncb call restricted to that stage.
+    def _stage(self, data, labels, device, **opts):
+        """One ``ncb_compare`` on ``data`` (positions, reads, vars) with the engine's options
+        replaced by ``opts`` for the call."""
+        engine = self._engine(device)
+        keep = dict(tests=engine.opts.tests, input_standardised=bool(engine.opts.input_standardised))
+        engine.configure(**opts)
+        try:
+            dev_data = torch.as_tensor(data).to(device=engine.device, dtype=torch.float32).contiguous()
+            return engine.compare_dense(dev_data, torch.from_numpy(labels).to(engine.device)).numpy()
+        finally:
+            engine.configure(**keep)
+
+    def _stage_device(self, device=None):
+        if isinstance(device, str) and device.startswith('cuda'):
+            return device
+        if self._engines:
+            return f'cuda:{next(iter(self._engines))}'
+        return 'cuda:0'
+
+    def _add_shift_stats(self, results, data, conditions, device):
+        """comparisons.py:406-433: mean, lower median and population sd of every variable per
+        condition, on the values as given."""
+        cond = _to_numpy(conditions)
+        labels = make_labels(np.zeros_like(cond), cond)
+        res = self._stage(data, labels, device, tests=0, input_standardised=True)
+        for column, row in shift_columns(self._motor_dwell_offset > 0):
+            results[column] = torch.from_numpy(res['stats'][row].copy())
+
+    def _nonparametric_test(self, test, test_data, conditions):
+        """comparisons.py:218-252 on filtered, standardised data (vars beyond intensity and dwell
+        are ignored, as there)."""
+        names = {'mann_whitney': 'MW', 'MW': 'MW', 'kolmogorov_smirnov': 'KS', 'KS': 'KS',
+                 't_test': 'TT', 'TT': 'TT'}
+        if test not in names:
+            raise NanocomporeError("Invalid statistical method name (MW, KS, TT)")
+        key = names[test]
+        cond = _to_numpy(conditions)
+        labels = make_labels(np.zeros_like(cond), cond)
+        data = torch.as_tensor(test_data)[:, :, :2]
+        res = self._stage(data, labels, self._stage_device(), tests=tests_mask([key]), input_standardised=True)
+        a, b = _NONPARAMETRIC[key]
+        return {f'{test}_intensity_pvalue': list(res['pvalues'][L.PV[a]]),
+                f'{test}_dwell_pvalue': list(res['pvalues'][L.PV[b]])}
+
+    def _gmm_test_split(self, data, samples, conditions, device):
+        """comparisons.py:338-392 on filtered, standardised data of 2 or 3 variables: both mixture
+        fits, BIC gate, contingency, counts, LOR, chi-squared."""
+        labels = make_labels(_to_numpy(samples), _to_numpy(conditions))
+        res = self._stage(data, labels, device, tests=tests_mask(['GMM'], self._with_logit),
+                          input_standardised=True)
+        n = res['status'].size
+        return self._test_columns('GMM', res['pvalues'], res['stats'], res['counts'],
+                                  np.zeros(n, dtype=np.int32), None)
+
+    def _split_by_ndim(self, test_data):
+        """comparisons.py:395-403: positions where at least 90 % of the reads with an intensity also
+        carry a motor dwell are fitted in 3 variables, the others in 2."""
+        valid = ~torch.isnan(test_data)
+        with_motor = (valid[:, :, INTENSITY] & valid[:, :, MOTOR]).sum(1)
+        use_motor = with_motor >= 0.9 * valid[:, :, INTENSITY].sum(1)
+        return test_data[use_motor], test_data[~use_motor][:, :, :MOTOR], (~use_motor).int()
+
+    def _gmm_test(self, test_data, samples, conditions, device):
+        """comparisons.py:285-335: with a motor-dwell column the positions are split by
+        ``_split_by_ndim``, each part goes through ``_gmm_test_split`` and the columns are merged back
+        in position order.  (``compare_transcript`` does not come through here: the kernels make the
+        same split per position inside one call.)"""
+        if self._motor_dwell_offset == 0:
+            return self._gmm_test_split(test_data, samples, conditions, device)
+        dim3, dim2, split = self._split_by_ndim(test_data)
+        parts = {}
+        if dim3.shape[0] > 0:
+            parts[0] = self._gmm_test_split(dim3, samples, conditions, device)
+        if dim2.shape[0] > 0:
+            parts[1] = self._gmm_test_split(dim2, samples, conditions, device)
+        split = _to_numpy(split)
+        merged = {}
+        for column in {c for part in parts.values() for c in part}:
+            cursor = {0: 0, 1: 0}
+            values = []
+            for which in split:
+                values.append(parts[int(which)][column][cursor[int(which)]])
+                cursor[int(which)] += 1
+            merged[column] = values
+        return merged
+
+    def _get_mod_cluster(self, contingency):
+        """comparisons.py:564-605: the cluster in which the depleted condition has the smaller share
+        of its reads is the modified one (ties: cluster 0)."""
+        contingency = torch.as_tensor(contingency)
+        totals = contingency.sum(2).to(torch.uint32)
+        share = contingency / totals.unsqueeze(2)
+        return share[:, self._depleted_condition_id(), :].argmin(1)
+
+    def _get_cluster_counts(self, contingency, samples, predictions):
+        """comparisons.py:477-517: reads of every sample in the modified / the other cluster; a NaN
+        prediction (read not in the fit) counts for neither."""
+        predictions = torch.as_tensor(predictions)
+        samples = torch.as_tensor(samples)
+        mod = self._get_mod_cluster(contingency)[:, None]
+        counts = {}
+        for label, sid in self._config.get_sample_ids().items():
+            pred = predictions[:, samples == sid]
+            in_fit = (~torch.isnan(pred.to(torch.float64))).sum(1)
+            n_mod = (pred == mod).sum(1)
+            counts[f'{label}_mod'] = n_mod.cpu().numpy().astype(np.uint32)
+            counts[f'{label}_unmod'] = (in_fit - n_mod).cpu().numpy().astype(np.uint32)
+        return counts
+
+    def _get_soft_cluster_counts(self, contingency, samples, cluster_probs):
+        """comparisons.py:520-561: the posterior mass of every sample in the modified / the other
+        cluster (NaN posteriors add nothing)."""
+        cluster_probs = torch.as_tensor(cluster_probs)
+        samples = torch.as_tensor(samples)
+        B, N, _ = cluster_probs.shape
+        mod = self._get_mod_cluster(contingency)[:, None, None].expand(B, N, 1)
+        p_mod = torch.gather(cluster_probs, 2, mod).squeeze(2)
+        p_other = torch.gather(cluster_probs, 2, 1 - mod).squeeze(2)
+        counts = {}
+        for label, sid in self._config.get_sample_ids().items():
+            mask = samples == sid
+            counts[f'{label}_mod'] = p_mod[:, mask].nansum(1).cpu().numpy()
+            counts[f'{label}_unmod'] = p_other[:, mask].nansum(1).cpu().numpy()
+        return counts
 
     def compare_transcripts(self, items, device):
         """
@@ -307,8 +440,9 @@ class TranscriptComparator:
         else:
             weights = [1] * (2 * context + 1)
         if self._context_engine is None:
-            raise NanocomporeError("no libncb engine: the context combination runs on the GPU "
-                                   "(nanocompore_b200 has no CPU path)")
+            # called on its own (the reference's tests do, tests/test_comparisons.py:157-206): the
+            # combination runs on the device of the comparator's engine, cuda:0 if none exists yet
+            self._engine(self._stage_device())
         if context > L.NCB_CTX_MAX:
             raise NanocomporeError(f"sequence_context {context} is larger than NCB_CTX_MAX = {L.NCB_CTX_MAX}")
         pos = np.asarray(pos).astype(np.int64)

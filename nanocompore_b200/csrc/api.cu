@@ -133,6 +133,8 @@ void ncb_default_opts(ncb_opts *o) {
     o->diagnostics = 0;
     o->em_tol = 1e-3;
     o->reg_covar = 1e-6;
+    o->input_standardised = 0;
+    o->reserved = 0;
 }
 
 static int check_opts(ncb_handle *h, const ncb_opts *o) {
@@ -141,7 +143,8 @@ static int check_opts(ncb_handle *h, const ncb_opts *o) {
     if (o->depleted_condition != 0 && o->depleted_condition != 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: depleted_condition must be 0 or 1");
     if (o->em_max_iter < 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: em_max_iter < 1");
     if (o->cluster_counts < NCB_COUNTS_NONE || o->cluster_counts > NCB_COUNTS_SOFT) return fail(h, NCB_ERR_INVALID, "ncb_opts: cluster_counts");
-    if (o->em_fp64 != 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: em_fp64 is reserved and must be 1");
+    if (o->em_fp64 != 0 && o->em_fp64 != 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: em_fp64 must be 0 or 1");
+    if (o->input_standardised != 0 && o->input_standardised != 1) return fail(h, NCB_ERR_INVALID, "ncb_opts: input_standardised must be 0 or 1");
     if (!(o->em_tol >= 0.0) || !(o->reg_covar >= 0.0) || o->em_tol > 1e300 || o->reg_covar > 1e300)
         return fail(h, NCB_ERR_INVALID, "ncb_opts: em_tol and reg_covar must be finite and >= 0");
     if (o->min_coverage < 0) return fail(h, NCB_ERR_INVALID, "ncb_opts: min_coverage < 0");
@@ -293,6 +296,8 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     a.dwell_is_raw = o.dwell_is_raw;
     a.cluster_counts = o.cluster_counts;
     a.em_max_iter = o.em_max_iter;
+    a.em_fp32 = o.em_fp64 ? 0 : 1;
+    a.input_standardised = o.input_standardised;
     a.em_tol = o.em_tol;
     a.reg_covar = o.reg_covar;
 

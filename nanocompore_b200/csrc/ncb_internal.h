@@ -24,6 +24,8 @@ struct NcbDeviceArgs {
     int32_t dwell_is_raw;
     int32_t cluster_counts;
     int32_t em_max_iter;
+    int32_t em_fp32;             // 1: float32 E-step (ncb_opts.em_fp64 == 0)
+    int32_t input_standardised;  // 1: no outlier rule, no scaling (ncb_opts.input_standardised)
     double em_tol;
     double reg_covar;
     // output

@@ -254,7 +254,8 @@ class Engine:
 
     def __init__(self, device=0, *, tests=('GMM', 'KS'), n_samples=4, depleted_condition=0,
                  min_coverage=0, dwell_is_raw=False, cluster_counts='hard', with_logit=False,
-                 em_max_iter=100, em_tol=1e-3, reg_covar=1e-6, lib_path=None):
+                 em_max_iter=100, em_tol=1e-3, reg_covar=1e-6, em_fp64=True, input_standardised=False,
+                 lib_path=None):
         if not torch.cuda.is_available():
             raise RuntimeError("nanocompore_b200 needs a CUDA device: there is no CPU fallback")
         self.lib = L.load(lib_path)
@@ -272,7 +273,8 @@ class Engine:
         self.configure(tests=tests, n_samples=n_samples, depleted_condition=depleted_condition,
                        min_coverage=min_coverage, dwell_is_raw=dwell_is_raw,
                        cluster_counts=cluster_counts, with_logit=with_logit,
-                       em_max_iter=em_max_iter, em_tol=em_tol, reg_covar=reg_covar, _apply=False)
+                       em_max_iter=em_max_iter, em_tol=em_tol, reg_covar=reg_covar, em_fp64=em_fp64,
+                       input_standardised=input_standardised, _apply=False)
         rc = self.lib.ncb_create(C.byref(self._handle), self.device_index, C.byref(self.opts))
         if rc != L.NCB_OK:
             self._handle = C.c_void_p()
@@ -281,7 +283,7 @@ class Engine:
     # ------------------------------------------------------------------ options
     def configure(self, *, tests=None, n_samples=None, depleted_condition=None, min_coverage=None,
                   dwell_is_raw=None, cluster_counts='__keep__', with_logit=None, em_max_iter=None,
-                  em_tol=None, reg_covar=None, _apply=True):
+                  em_tol=None, reg_covar=None, em_fp64=None, input_standardised=None, _apply=True):
         o = self.opts
         if tests is not None:
             logit = bool(with_logit) if with_logit is not None else bool(o.tests & L.NCB_TEST_LOGIT)
@@ -304,6 +306,10 @@ class Engine:
             o.em_tol = float(em_tol)
         if reg_covar is not None:
             o.reg_covar = float(reg_covar)
+        if em_fp64 is not None:
+            o.em_fp64 = int(bool(em_fp64))
+        if input_standardised is not None:
+            o.input_standardised = int(bool(input_standardised))
         if _apply:
             self._check(self.lib.ncb_set_opts(self._handle, C.byref(o)))
 

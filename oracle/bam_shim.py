@@ -95,4 +95,16 @@ class AlignmentFile:
         return len(self.fetch(reference))
 
     def get_index_statistics(self):
-        raise NotImplementedError
+        """pysam's per-contig index statistics (common.py:284-295 reads ``contig`` and ``mapped``):
+        records placed on the contig whose unmapped flag is clear."""
+        from collections import namedtuple
+        Stat = namedtuple('IndexStats', 'contig mapped unmapped total')
+        out = []
+        for rid, name in enumerate(self.references):
+            mapped = sum(1 for r in self._reads if r.reference_id == rid and not (r.flag & 4))
+            unmapped = sum(1 for r in self._reads if r.reference_id == rid and (r.flag & 4))
+            out.append(Stat(name, mapped, unmapped, mapped + unmapped))
+        return out
+
+    def close(self):
+        pass

@@ -166,9 +166,14 @@ def test_too_many_reads_is_reported(engine_factory):
     rng = np.random.default_rng(1)
     data = rng.standard_normal((2, L.NCB_MAX_READS + 8, 2)).astype(np.float32)
     lab = torch.from_numpy(make_labels(np.zeros(data.shape[1]), np.arange(data.shape[1]) % 2)).cuda()
-    res = eng.compare_dense(torch.from_numpy(data).cuda(), lab).numpy()
+    from nanocompore_b200.engine import Results
+    out = Results(2, 4, torch.device('cuda'))
+    with pytest.raises(L.NcbError) as err:          # ncb_wait reports it (include/ncb.h)
+        eng.compare_dense(torch.from_numpy(data).cuda(), lab, out)
+    assert err.value.code == L.NCB_ERR_TOO_MANY_READS
+    res = out.numpy()
     assert ((res['status'] & L.NCB_POS_TOO_MANY_READS) != 0).all()
-    assert np.isnan(res['pvalues']).all()
+    assert np.isnan(res['pvalues']).all() and np.isnan(res['stats']).all() and (res['counts'] == 0).all()
 
 
 def test_soft_cluster_counts(engine_factory):
