@@ -506,6 +506,33 @@ def run_gpu_arm(args):
     eng0.set_timing(False)
     fp64_peak = eng0.probe_fp64_peak()   # DFMA microbenchmark on this device, TFLOP/s
 
+    # ---- the float32 E-step mode (ncb_opts.em_fp64 = 0, the reference's dtype): same batches, resident;
+    # how often it decides differently from the fp64 definition
+    r64 = eng0.compare_csr(dev_pool[0], res_dev[0]).numpy()
+    rig.configure(em_fp64=False)
+    rig.resident(dev_pool, order_w, res_dev)
+    ms32_local, tested32 = rig.resident(dev_pool, order_k, res_dev)
+    ms32 = max_over_ranks(ms32_local)
+    eng0.set_timing(True)
+    for b in range(min(n_pool, 6)):
+        eng0.compare_csr(dev_pool[b], res_dev[0], wait=False)
+    totals32 = eng0.timing_totals()
+    eng0.set_timing(False)
+    r32 = eng0.compare_csr(dev_pool[0], res_dev[0]).numpy()
+    rig.configure(em_fp64=True)
+    ok64 = (r64['status'] & L.NCB_POS_DROP_MASK) == 0
+    p64, p32 = r64['pvalues'][L.PV['GMM_CHI2']][ok64], r32['pvalues'][L.PV['GMM_CHI2']][ok64]
+    gate_flips = int((np.isnan(p64) != np.isnan(p32)).sum())
+    both = ~np.isnan(p64) & ~np.isnan(p32)
+    count_flips = int((r64['counts'][:, :, ok64] != r32['counts'][:, :, ok64]).any(axis=(0, 1)).sum())
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p_off = int((~np.isclose(np.log10(p64[both]), np.log10(p32[both]), rtol=1e-5, atol=1e-8)).sum())
+    em_fp32 = {"value": sum_over_ranks(float(tested32)) / (ms32 / 1000.0), "unit": UNIT,
+               "ms_per_step": ms32 / K, "ms_mixture_per_batch": totals32['ms_gmm'] / max(totals32['batches'], 1),
+               "vs_fp64_definition": {"positions": int(ok64.sum()), "bic_gate_flips": gate_flips,
+                                      "positions_with_other_counts": count_flips,
+                                      "chi2_pvalues_off_1e-5": p_off}}
+
     # ---- e2e: the whole job from pinned host batches to corrected results --------------------
     res_host = [Results(P, 4, None) for _ in range(NSLOT)]
     pv_rows = [L.PV['KS_INTENSITY'], L.PV['KS_DWELL'], L.PV['GMM_CHI2']]
@@ -673,6 +700,7 @@ def run_gpu_arm(args):
                 "stages_ms": stages, "includes": "H2D, kernels, D2H per batch; BH correction over all ranks' rows; "
                                                  "q-values to the host; gather of keys + q-values on rank 0"},
         "e2e_f32_wire": e2e_f32,
+        "em_fp32": dict(em_fp32, speedup_of_mixture_kernel=ms_gmm / em_fp32["ms_mixture_per_batch"]),
         "parity_spot_check": check,
         "gpu_launches": total_launches,
         "lpt": lpt,
