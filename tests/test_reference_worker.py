@@ -36,6 +36,8 @@ def test_reference_worker_loop_with_its_own_comparator(tmp_path):
 @pytest.mark.gpu
 def test_reference_worker_loop_with_the_b200_comparator(tmp_path):
     from nanocompore_b200.comparisons import TranscriptComparator
+    (tmp_path / 'cpu').mkdir()
+    (tmp_path / 'gpu').mkdir()
     want, _ = ref_worker.run_worker(tmp_path / 'cpu')
     got, messages = ref_worker.run_worker(tmp_path / 'gpu', comparator_cls=TranscriptComparator, device='cuda:0')
     assert not [m for m in messages if m[0] == 'error'], messages
