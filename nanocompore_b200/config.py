@@ -11,6 +11,7 @@ DEFAULT_DOWNSAMPLE_HIGH_COVERAGE = 5000
 DEFAULT_COMPARISON_METHODS = ['GMM', 'KS']
 DEFAULT_KIT = 'RNA002'
 DEFAULT_MAX_INVALID_KMERS_FREQ = 0.1
+DEFAULT_CORRECTION_METHOD = 'fdr_bh'
 HARD_ASSIGNMENT = 'hard'
 SOFT_ASSIGNMENT = 'soft'
 
@@ -34,6 +35,11 @@ class PathConfig:
             raise ValueError('sequence_context must be >= 0 and <= 4')
         if config.get('motor_dwell_offset', 0) < 0:
             raise ValueError('motor_dwell_offset must be >= 0')
+        # the reference's schema accepts exactly one value (config.py:175): refused here, when the
+        # configuration is read, not when the correction runs at the end of a job
+        if config.get('correction_method', DEFAULT_CORRECTION_METHOD) != DEFAULT_CORRECTION_METHOD:
+            raise ValueError(f"correction_method must be {DEFAULT_CORRECTION_METHOD!r} "
+                             f"(got {config.get('correction_method')!r})")
         self._config = config
 
     def get_data(self):
@@ -50,6 +56,9 @@ class PathConfig:
 
     def get_sequence_context_weights(self):
         return self._config.get('sequence_context_weights', 'uniform')
+
+    def get_correction_method(self):
+        return self._config.get('correction_method', DEFAULT_CORRECTION_METHOD)
 
     def get_cluster_counts(self):
         return self._config.get('cluster_counts', HARD_ASSIGNMENT)

@@ -76,14 +76,15 @@ def test_auto_routing_columns():
 
 
 def test_context_columns_need_the_gpu():
-    """The context combination is a libncb kernel (ncb_context_combine): without an engine the
-    frame cannot be assembled -- there is no host path to fall back to."""
-    from nanocompore_b200.comparisons import NanocomporeError
+    """The context combination is a libncb kernel (ncb_context_combine): called on its own it makes an
+    engine on cuda:0, and without a GPU that fails -- there is no host path to fall back to."""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
     rng = np.random.default_rng(3)
     P = 60
     status, pv, st, counts = columns(P, rng)
     cfg = PathConfig(dict(data=DATA, depleted_condition='kd', comparison_methods=['KS'], sequence_context=2))
-    with pytest.raises(NanocomporeError, match="no CPU path"):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         TranscriptComparator(cfg, Worker())._assemble(Transcript, torch.arange(P, dtype=torch.int16),
                                                       status, pv, st, counts, False)
 
@@ -97,3 +98,17 @@ def test_too_many_reads_raises():
     with pytest.raises(NanocomporeError):
         TranscriptComparator(cfg, Worker())._assemble(Transcript, torch.arange(5, dtype=torch.int16),
                                                       status, pv, st, counts, False)
+
+
+def test_correction_method_is_checked_when_the_configuration_is_read():
+    """config.py:175 admits 'fdr_bh' only: anything else is refused up front, with the key's name."""
+    import pytest
+    from nanocompore_b200.config import PathConfig
+    from nanocompore_b200.postprocessing import check_correction_method
+    base = dict(data={'kd': {'kd1': {'bam': 'a'}}, 'wt': {'wt1': {'bam': 'b'}}}, depleted_condition='kd')
+    assert PathConfig(base).get_correction_method() == 'fdr_bh'
+    assert PathConfig(dict(base, correction_method='fdr_bh')).get_correction_method() == 'fdr_bh'
+    with pytest.raises(ValueError, match='correction_method'):
+        PathConfig(dict(base, correction_method='bonferroni'))
+    with pytest.raises(ValueError, match='holm'):
+        check_correction_method('holm')
