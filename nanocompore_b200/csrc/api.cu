@@ -35,7 +35,7 @@ struct ncb_handle {
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
-    DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n, zbuf3, gmm_n3;
+    DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n, zbuf3, gmm_n3, mw_scratch;
     DevBuf wl_count, wl_list;
     DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch, kw_rtab;
     DevBuf fdr_scratch, fdr_p, fdr_q;
@@ -217,7 +217,7 @@ void ncb_destroy(ncb_handle *h) {
     guard.enter(h->device);
     DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
                      &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
-                     &h->ks_h, &h->zbuf, &h->gmm_n, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
+                     &h->ks_h, &h->zbuf, &h->gmm_n, &h->mw_scratch, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
                      &h->kw_bin, &h->kw_fetch, &h->kw_rtab, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d,
                      &h->ctx_tx, &h->ctx_track, &h->ctx_idx, &h->ctx_p, &h->ctx_tracks, &h->ctx_out, &h->ctx_status};
@@ -387,6 +387,15 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
             a.zbuf3 = (float *)h->zbuf3.ptr;
             a.gmm_n3 = (int32_t *)h->gmm_n3.ptr;
         }
+    }
+    // SciPy enumerates the exact Mann-Whitney distribution when a sample has at most 8 values
+    // (_mannwhitneyu.py:212-223): reachable when the coverage filter lets such samples through (the
+    // outlier rule removes a few reads more, hence the margin).  Only then the scratch exists.
+    if ((o.tests & NCB_TEST_MW) && o.min_coverage <= 16) {
+        const int64_t len = NCB_MW_SCRATCH_PER_SM * h->sm_count;
+        ENSURE(h->mw_scratch, (size_t)len * sizeof(double));
+        a.mw_scratch = (double *)h->mw_scratch.ptr;
+        a.mw_scratch_len = len;
     }
     ENSURE(h->wl_count, NCB_WL_COUNTERS * sizeof(int32_t));
     ENSURE(h->wl_list, (size_t)P * NCB_NUM_CLASSES * sizeof(int32_t));

@@ -40,6 +40,10 @@ struct NcbDeviceArgs {
     int32_t *gmm_n;              // [P] reads in the 2-variable fit, 0 = none on this position
     float *zbuf3;                // 3-variable batches: standardised motor dwell per entry
     int32_t *gmm_n3;             // 3-variable batches: [P] reads in the 3-variable fit, 0 = none
+    // scratch: rows of the exact Mann-Whitney counting recurrence that do not fit on chip, one per
+    // resident group (4 CAP + 8 doubles of the group's size class); NULL when the batch cannot need it
+    double *mw_scratch;
+    int64_t mw_scratch_len;      // doubles
     // scratch: exact-KS work items, one per (variable, position): index v * P + p
     int32_t *ks_n0;
     int32_t *ks_n1;
@@ -53,6 +57,10 @@ struct NcbDeviceArgs {
 //   class 4   : one 256-thread CTA per position, 8 entries per thread
 //   class 5   : one 512-thread CTA per position, 8 entries per thread
 //   class 6   : one 1024-thread CTA per position, 10 entries per thread
+// doubles of the Mann-Whitney scratch per SM: (resident groups per SM) x (4 CAP + 8) is 8 320, 24 768, 32 896,
+// 32 832, 32 800, 32 784 and 40 968 for the seven size classes (the kernels of one handle's classes run one
+// after the other on its stream, so they share the rows); a group whose row would not fit keeps the flag
+#define NCB_MW_SCRATCH_PER_SM (4 * (int64_t)NCB_MAX_READS + 8)
 #define NCB_TIMING_LOG_MAX 4096   /* batches kept in a handle's timing log */
 enum { NCB_NUM_CLASSES = 7, NCB_NUM_PHASES = 4 };   // phases: statistics / mixture, 2 / 3 variables
 #define NCB_WL_COUNTERS (NCB_NUM_CLASSES * (1 + NCB_NUM_PHASES))

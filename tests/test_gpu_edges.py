@@ -142,3 +142,37 @@ def test_declared_max_entries_skips_classes_but_not_results(engine_factory):
     same = ~over
     assert (res['pvalues'][L.PV['KS_INTENSITY']][same] == want['pvalues'][L.PV['KS_INTENSITY']][same]).all() or \
         np.array_equal(np.isnan(res['pvalues'][L.PV['KS_INTENSITY']][same]), np.isnan(want['pvalues'][L.PV['KS_INTENSITY']][same]))
+
+
+@pytest.mark.parametrize('n_small,n_large', [(3, 40), (8, 120), (5, 400), (8, 900), (6, 1800), (8, 3500), (7, 6000)])
+def test_exact_mann_whitney_small_against_large(engine_factory, n_small, n_large):
+    """A sample of at most 8 values without ties: SciPy enumerates the null distribution whatever the
+    size of the other sample (_mannwhitneyu.py:212-223).  The counting row of such a position does not
+    fit on chip; it lives in the handle's global scratch -- a p-value, not NaN + a status bit."""
+    from oracle import stats as ostats
+    from oracle.nonparametric import nonparametric_test
+    from parity_utils import assert_pvalues_close
+    eng = engine_factory(tests=('MW',), min_coverage=0)
+    rng = np.random.default_rng(n_small * 10007 + n_large)
+    P, R = 12, n_small + n_large
+    data = rng.standard_normal((P, R, 2)).astype(np.float32)
+    # the small sample is condition 0 on even positions' layout, condition 1 on the odd seed
+    cond = np.zeros(R, dtype=np.int64)
+    if n_large % 2:
+        cond[:n_large] = 1
+    else:
+        cond[n_small:] = 1
+    shift = np.linspace(-1.2, 1.2, P).astype(np.float32)
+    small = (cond == 0) if (cond == 0).sum() == n_small else (cond == 1)
+    data[:, small, :] += shift[:, None, None]
+    samples = cond * 2
+    lab = torch.from_numpy(make_labels(samples, cond)).cuda()
+    res = eng.compare_dense(torch.from_numpy(data).cuda(), lab, diagnostics=True).numpy()
+    std_data, _, bad, _ = ostats.outlier_standardise(data)
+    assert not bad.any()
+    assert ((res['status'] & L.NCB_POS_MW_EXACT_SKIPPED) == 0).all()
+    want = nonparametric_test('MW', std_data, cond)
+    assert_pvalues_close(res['pvalues'][L.PV['MW_INTENSITY']], want['MW_intensity_pvalue'], 'exact MW intensity p')
+    assert_pvalues_close(res['pvalues'][L.PV['MW_DWELL']], want['MW_dwell_pvalue'], 'exact MW dwell p')
+    # (float32 values of a large sample may collide: SciPy and the kernel then both take the asymptotic form)
+    assert (res['diag_i64'][L.DI['MW_TIE_INTENSITY']] == 0).sum() >= P // 2
