@@ -254,6 +254,16 @@ int ncb_ks_exact_pvalues(ncb_handle *h, int64_t n, const int32_t *n0, const int3
 int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
                int memory, void *stream);
 
+/* The same correction for ONE VALUE RANGE of a column whose rows are spread over several GPUs (the
+ * reference corrects a column over the rows of the whole run, postprocessing.py:209-285): the column
+ * holds m_total numbers (NaNs not counted) of which n_above are larger than every number passed
+ * here.  q[i] = min over the passed values p_j >= p_i of p_j * m_total / rank_j with rank_j the rank of
+ * p_j in the whole column; the caller completes it with the minimum of the ranges above (one number
+ * per range) -- nanocompore_b200/sharding.py:fdr_columns.  m_total < 0: the values are the whole
+ * column (= ncb_bh_fdr). */
+int ncb_bh_fdr_segment(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
+                       int64_t n_above, int64_t m_total, int memory, void *stream);
+
 /* Sequence-context combination of p-value columns (Hou's weighted Fisher combination of
  * dependent p-values): replaces TranscriptComparator._combine_context_pvalues
  * (comparisons.py:436-474) with cross_corr_matrix (627-651) and combine_pvalues_hou (659-705),

@@ -48,7 +48,7 @@ NCB_DF_ROWS = 17
 
 EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_results_host_bytes',
-           'ncb_pack_fill_i16', 'ncb_pack_rows_fill_i16', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr',
+           'ncb_pack_fill_i16', 'ncb_pack_rows_fill_i16', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr', 'ncb_bh_fdr_segment',
            'ncb_context_combine',
            'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals',
            'ncb_pack_count', 'ncb_pack_fill', 'ncb_pack_rows_count', 'ncb_pack_rows_fill',
@@ -119,6 +119,8 @@ def load(path=None):
     lib.ncb_ks_exact_pvalues.restype = C.c_int
     lib.ncb_bh_fdr.argtypes = [vp, i64, vp, vp, C.c_double, C.c_int, vp]
     lib.ncb_bh_fdr.restype = C.c_int
+    lib.ncb_bh_fdr_segment.argtypes = [vp, i64, vp, vp, C.c_double, i64, i64, C.c_int, vp]
+    lib.ncb_bh_fdr_segment.restype = C.c_int
     lib.ncb_context_combine.argtypes = [vp, i64, vp, vp, i32, vp, i32, vp, vp, vp, C.c_int, vp]
     lib.ncb_context_combine.restype = C.c_int
     lib.ncb_kernel_launches.argtypes = [vp]

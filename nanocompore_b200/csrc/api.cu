@@ -18,6 +18,7 @@ struct DevBuf {
 struct ncb_handle {
     int device = 0;
     int sm_count = 148;
+    bool gmm_split = true;   // warp size classes: the three-kernel mixture fit (NCB_GMM_SPLIT=0: the fused kernel, for A/B runs)
     ncb_opts opts;
     std::string err;
     int64_t launches = 0;
@@ -35,7 +36,7 @@ struct ncb_handle {
     // grow-only device buffers
     DevBuf in_signal, in_label, in_offsets;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
-    DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n, zbuf3, gmm_n3, mw_scratch;
+    DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n, gmm_rec, zbuf3, gmm_n3, mw_scratch;
     DevBuf wl_count, wl_list;
     DevBuf kw_hist, kw_cursor, kw_list, kw_bin, kw_fetch, kw_rtab;
     DevBuf fdr_scratch, fdr_p, fdr_q;
@@ -197,6 +198,8 @@ int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
         return NCB_ERR_CUDA;
     }
     *h->flag_host = 0;
+    const char *gs = getenv("NCB_GMM_SPLIT");
+    if (gs && gs[0] == '0') h->gmm_split = false;
     const char *t = getenv("NCB_TIMING");
     h->timing = (t && t[0] == '1') ? 1 : 0;
     *out = h;
@@ -217,7 +220,7 @@ void ncb_destroy(ncb_handle *h) {
     guard.enter(h->device);
     DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
                      &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
-                     &h->ks_h, &h->zbuf, &h->gmm_n, &h->mw_scratch, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
+                     &h->ks_h, &h->zbuf, &h->gmm_n, &h->gmm_rec, &h->mw_scratch, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
                      &h->kw_bin, &h->kw_fetch, &h->kw_rtab, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d,
                      &h->ctx_tx, &h->ctx_track, &h->ctx_idx, &h->ctx_p, &h->ctx_tracks, &h->ctx_out, &h->ctx_status};
@@ -381,6 +384,10 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
         ENSURE(h->gmm_n, (size_t)P * sizeof(int32_t));
         a.zbuf = (float2 *)h->zbuf.ptr;
         a.gmm_n = (int32_t *)h->gmm_n.ptr;
+        if (h->gmm_split) {
+            ENSURE(h->gmm_rec, (size_t)P * NCB_GMM_REC * sizeof(double));
+            a.gmm_rec = (double *)h->gmm_rec.ptr;
+        }
         if (n_vars == 3) {
             ENSURE(h->zbuf3, (size_t)E * sizeof(float));
             ENSURE(h->gmm_n3, (size_t)P * sizeof(int32_t));
@@ -551,10 +558,12 @@ int ncb_ks_exact_pvalues(ncb_handle *h, int64_t n, const int32_t *n0, const int3
     return NCB_OK;
 }
 
-int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
-               int memory, void *stream) {
+int ncb_bh_fdr_segment(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
+                       int64_t n_above, int64_t m_total, int memory, void *stream) {
     if (!h) return NCB_ERR_INVALID;
     if (n < 0 || n > 0x7fffffffLL) return fail(h, NCB_ERR_INVALID, "ncb_bh_fdr: n out of range");
+    if (n_above < 0 || (m_total >= 0 && m_total < n_above))
+        return fail(h, NCB_ERR_INVALID, "ncb_bh_fdr_segment: n_above / m_total out of range");
     if (n == 0) return NCB_OK;
     if (!pvalues || !qvalues) return fail(h, NCB_ERR_INVALID, "ncb_bh_fdr: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
@@ -570,7 +579,7 @@ int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues,
         dp = (const double *)h->fdr_p.ptr;
         dq = (double *)h->fdr_q.ptr;
     }
-    int k = ncb_launch_bh_fdr(n, dp, dq, scale, h->fdr_scratch.ptr, h->fdr_scratch.bytes, s);
+    int k = ncb_launch_bh_fdr(n, dp, dq, scale, n_above, m_total, h->fdr_scratch.ptr, h->fdr_scratch.bytes, s);
     if (k < 0) return fail(h, NCB_ERR_CUDA, "BH FDR launch", cudaGetLastError());
     h->launches += k;
     if (memory == NCB_MEM_HOST) {
@@ -578,6 +587,11 @@ int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues,
         CK(cudaStreamSynchronize(s));
     }
     return NCB_OK;
+}
+
+int ncb_bh_fdr(ncb_handle *h, int64_t n, const double *pvalues, double *qvalues, double scale,
+               int memory, void *stream) {
+    return ncb_bh_fdr_segment(h, n, pvalues, qvalues, scale, 0, -1, memory, stream);
 }
 
 int ncb_context_combine(ncb_handle *h, int64_t n_tx, const int64_t *tx_offsets, const int64_t *pos,

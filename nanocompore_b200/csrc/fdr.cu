@@ -35,16 +35,19 @@ __global__ void bh_keys_kernel(int64_t n, const double *p, u64 *keys, uint32_t *
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_valid, local);
 }
 
-// raw q in descending-p order: position s holds ascending rank m - s
+// raw q in descending-p order: position s holds ascending rank M - above - s, where the column has M
+// numbers in all and `above` of them are larger than every number of this segment (a whole column:
+// M = m, above = 0)
 __global__ void bh_raw_kernel(int64_t n, const double *p, const uint32_t *idx_sorted,
-                              const unsigned long long *n_valid, double *qraw) {
+                              const unsigned long long *n_valid, double *qraw, int64_t above, int64_t m_total) {
     const int64_t m = (int64_t)*n_valid;
+    const int64_t M = m_total < 0 ? m : m_total;
     for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n;
          s += (int64_t)gridDim.x * blockDim.x) {
         double q = __longlong_as_double(0x7ff0000000000000LL);   // +inf: neutral for min
         if (s < m) {
             double pv = p[idx_sorted[s]];
-            double ecdf = __ddiv_rn((double)(m - s), (double)m);
+            double ecdf = __ddiv_rn((double)(M - above - s), (double)M);
             q = __ddiv_rn(pv, ecdf);
         }
         qraw[s] = q;
@@ -109,8 +112,8 @@ size_t ncb_bh_fdr_scratch_bytes(int64_t n) {
     return bh_layout(n).total;
 }
 
-int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, void *scratch,
-                      size_t scratch_bytes, cudaStream_t s) {
+int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, int64_t above, int64_t m_total,
+                      void *scratch, size_t scratch_bytes, cudaStream_t s) {
     if (n <= 0) return 0;
     if (n > 0x7fffffffLL) return -1;
     BhLayout L = bh_layout(n);
@@ -128,7 +131,7 @@ int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, void 
     if (cub::DeviceRadixSort::SortPairsDescending(base + L.cub_tmp, tmp, keys_in, keys_out, idx_in,
                                                   idx_out, (int)n, 0, 64, s) != cudaSuccess)
         return -1;
-    bh_raw_kernel<<<blocks, 256, 0, s>>>(n, p, idx_out, nvalid, qraw);
+    bh_raw_kernel<<<blocks, 256, 0, s>>>(n, p, idx_out, nvalid, qraw, above, m_total);
     tmp = L.cub_bytes;
     if (cub::DeviceScan::InclusiveScan(base + L.cub_tmp, tmp, qraw, qmin, MinOp(), (int)n, s) !=
         cudaSuccess)

@@ -38,6 +38,8 @@ struct NcbDeviceArgs {
     // scratch: hand-over from the statistics kernel to the mixture kernel
     float2 *zbuf;                // standardised (intensity, dwell) per entry, NaN x = not in the fit
     int32_t *gmm_n;              // [P] reads in the 2-variable fit, 0 = none on this position
+    double *gmm_rec;             // [P][NCB_GMM_REC] hand-over between the three mixture kernels of the warp
+                                 // size classes (gmm_split.cu); NULL: the fused kernel takes those classes too
     float *zbuf3;                // 3-variable batches: standardised motor dwell per entry
     int32_t *gmm_n3;             // 3-variable batches: [P] reads in the 3-variable fit, 0 = none
     // scratch: rows of the exact Mann-Whitney counting recurrence that do not fit on chip, one per
@@ -62,7 +64,13 @@ struct NcbDeviceArgs {
 // after the other on its stream, so they share the rows); a group whose row would not fit keeps the flag
 #define NCB_MW_SCRATCH_PER_SM (4 * (int64_t)NCB_MAX_READS + 8)
 #define NCB_TIMING_LOG_MAX 4096   /* batches kept in a handle's timing log */
-enum { NCB_NUM_CLASSES = 7, NCB_NUM_PHASES = 4 };   // phases: statistics / mixture, 2 / 3 variables
+// phases (each has its own work counter per class): statistics / mixture, 2 / 3 variables; the mixture
+// phase of the warp classes is three kernels (gmm_split.cu): initialisation (the counter of
+// NCB_PHASE_GMM), EM passes, final pass
+enum { NCB_PHASE_STATS = 0, NCB_PHASE_GMM = 1, NCB_PHASE_STATS3 = 2, NCB_PHASE_GMM3 = 3, NCB_PHASE_GMM_EM = 4,
+       NCB_PHASE_GMM_FINAL = 5 };
+enum { NCB_NUM_CLASSES = 7, NCB_NUM_PHASES = 6 };
+#define NCB_GMM_REC 24   /* doubles per position in NcbDeviceArgs.gmm_rec */
 #define NCB_WL_COUNTERS (NCB_NUM_CLASSES * (1 + NCB_NUM_PHASES))
 static const int NCB_CLASS_CAP[NCB_NUM_CLASSES] = {128, 256, 512, 1024, 2048, 4096, NCB_MAX_READS};
 
@@ -111,11 +119,16 @@ int ncb_launch_ks_pvalues(int64_t n_problems, const int32_t *n0, const int32_t *
                           cudaStream_t s);
 // fills the handle's table of reciprocals (once, at ncb_create)
 int ncb_launch_ks_rtab(double *rtab, cudaStream_t s);
-int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, void *scratch,
-                      size_t scratch_bytes, cudaStream_t s);
+// `above`, `m_total`: the values are one value range of a longer column (ncb_bh_fdr_segment); a whole
+// column has above = 0, m_total = -1 (its own count of numbers)
+int ncb_launch_bh_fdr(int64_t n, const double *p, double *q, double scale, int64_t above, int64_t m_total,
+                      void *scratch, size_t scratch_bytes, cudaStream_t s);
 size_t ncb_bh_fdr_scratch_bytes(int64_t n);
 int ncb_launch_context(int64_t n_tx, int64_t n_rows, int64_t track_total, int32_t n_cols,
                        const int64_t *tx_offsets, const int64_t *track_offsets, const int32_t *idx,
                        const double *pvalues, double *tracks, double *combined, int32_t *status,
                        int32_t context, const double *weights, cudaStream_t s);
 int ncb_configure_kernels(void);  // cudaFuncSetAttribute for large dynamic shared memory
+// mixture fit of warp size class `cls` (0..2) as three kernels (gmm_split.cu); returns the number launched
+int ncb_configure_gmm_split(void);
+int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, int cls, int sm_count, cudaStream_t s);

@@ -63,24 +63,34 @@ inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
 
 }  // namespace
 
-// Message of the last failure on a handle.  Transcripts may be read from one handle by several
-// threads at once (the tables below are read-only after ncb_bam_open); only this text is written,
-// so its writers take a lock.
+// Message of the last failure on a handle, per calling thread.  Transcripts may be read from one
+// handle by several threads at once (the tables below are read-only after ncb_bam_open); each call
+// clears and sets the text of ITS thread, and ncb_bam_last_error returns the calling thread's: a
+// failure on one transcript is not wiped by a call that starts on another meanwhile.
 struct ErrorText {
-    std::mutex mu;
-    std::string text;
+    mutable std::mutex mu;
+    std::unordered_map<std::thread::id, std::string> by_thread;   // node-based: the strings stay in place
     ErrorText &operator=(const std::string &s) {
         std::lock_guard<std::mutex> g(mu);
-        text = s;
+        by_thread[std::this_thread::get_id()] = s;
         return *this;
     }
     ErrorText &operator=(const char *s) { return *this = std::string(s); }
     void clear() {
         std::lock_guard<std::mutex> g(mu);
-        if (!text.empty()) text.clear();
+        auto it = by_thread.find(std::this_thread::get_id());
+        if (it != by_thread.end()) it->second.clear();
     }
-    bool empty() const { return text.empty(); }
-    const char *c_str() const { return text.c_str(); }
+    bool empty() const {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = by_thread.find(std::this_thread::get_id());
+        return it == by_thread.end() || it->second.empty();
+    }
+    const char *c_str() const {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = by_thread.find(std::this_thread::get_id());
+        return it == by_thread.end() ? "" : it->second.c_str();
+    }
 };
 
 struct ncb_bam {

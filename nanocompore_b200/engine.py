@@ -417,19 +417,24 @@ class Engine:
             L.NCB_MEM_HOST, self._stream()))
         return out
 
-    def bh_fdr(self, pvalues, scale=1.0):
+    def bh_fdr(self, pvalues, scale=1.0, above=0, total=None):
         """Benjamini-Hochberg q-values, NaNs skipped (postprocessing.py:255-285).  Accepts a
-        numpy array (host) or a CUDA float64 tensor (stays on the device)."""
+        numpy array (host) or a CUDA float64 tensor (stays on the device).  ``above`` / ``total``:
+        the values are one value range of a column of ``total`` numbers, ``above`` of them larger
+        than all of these (``ncb_bh_fdr_segment``; the distributed correction of sharding.py)."""
+        m_total = -1 if total is None else int(total)
         if isinstance(pvalues, torch.Tensor) and pvalues.is_cuda:
             p = pvalues.contiguous().to(torch.float64)
             q = torch.empty_like(p)
-            self._check(self.lib.ncb_bh_fdr(self._handle, p.numel(), p.data_ptr(), q.data_ptr(),
-                                            float(scale), L.NCB_MEM_DEVICE, self._stream()))
+            self._check(self.lib.ncb_bh_fdr_segment(self._handle, p.numel(), p.data_ptr(), q.data_ptr(),
+                                                    float(scale), int(above), m_total, L.NCB_MEM_DEVICE,
+                                                    self._stream()))
             return q
         p = np.ascontiguousarray(pvalues, dtype=np.float64)
         q = np.empty_like(p)
-        self._check(self.lib.ncb_bh_fdr(self._handle, p.size, p.ctypes.data, q.ctypes.data,
-                                        float(scale), L.NCB_MEM_HOST, self._stream()))
+        self._check(self.lib.ncb_bh_fdr_segment(self._handle, p.size, p.ctypes.data, q.ctypes.data,
+                                                float(scale), int(above), m_total, L.NCB_MEM_HOST,
+                                                self._stream()))
         return q
 
     def context_combine(self, tx_offsets, pos, pvalues, context, weights):

@@ -9,11 +9,13 @@ longest-processing-time (LPT) bin packing on a work estimate, every rank runs it
 data-path collective (positions are independent), and the job ends with two exchanges over
 NCCL / NVLink (gloo in the CPU tests):
 
-  * ``fdr_columns``     Benjamini-Hochberg over the p-value columns of ALL ranks: column c goes to
-                        its owner rank (c mod world) in one all-to-all, the owner runs the GPU
-                        sort-scan (``ncb_bh_fdr``) over the whole column, a second all-to-all brings
-                        every rank the q-values of its own rows.  No rank holds more than its own
-                        rows plus the columns it owns.
+  * ``fdr_columns``     Benjamini-Hochberg over the p-value columns of ALL ranks as a sample sort:
+                        the value axis of a column is cut into one range per rank, an all-to-all
+                        brings every range to its rank, which runs the GPU sort-scan
+                        (``ncb_bh_fdr_segment``) with the ranks of the whole column; a second
+                        all-to-all brings every rank the q-values of its own rows.  Every rank does
+                        1 / world of every column (with whole columns on owner ranks, three ranks of
+                        eight sorted 5 x 10^8 values each while five idled: 0.9 s of a 3.1 s job).
   * ``gather_columns``  the result columns of every rank on one rank, rows sorted by a global key
                         (so the table does not depend on the sharding).
 
@@ -76,47 +78,79 @@ def _all_counts(n_local, device, group, world):
     return [int(c) for c in counts.tolist()]
 
 
+FDR_SAMPLE = 4096      # numbers every rank contributes to the splitter sample of a column
+
+
 def fdr_columns(cols, bh, group=None):
     """Benjamini-Hochberg q-values of p-value columns whose rows are spread over the ranks.
 
     ``cols``: float64 tensor [C, n_local], the columns of this rank's rows (NaN = not tested);
-    ``bh``: callable mapping a 1-D float64 tensor of p-values to its q-values, NaNs skipped
-    (``Engine.bh_fdr`` on a GPU).  Returns [C, n_local]: for every row of this rank the q-value it
-    has in the correction of the WHOLE column (all ranks' rows), as
+    ``bh``: callable ``bh(p, above=0, total=None)`` giving the q-values of a 1-D float64 tensor of
+    p-values, NaNs skipped, when they are one value range of a column of ``total`` numbers with
+    ``above`` larger ones elsewhere (``Engine.bh_fdr`` on a GPU, ``oracle.fdr.fdr_bh_segment`` in the
+    CPU tests).  Returns [C, n_local]: for every row of this rank the q-value it has in the
+    correction of the WHOLE column (all ranks' rows), as
     ``Postprocessor._multipletests_filter_nan`` (postprocessing.py:255-285) gives on the full table.
-    The result does not depend on how the rows are sharded."""
+    The result does not depend on how the rows are sharded.
+
+    Every rank does 1 / world of the work of every column (a sample sort): splitters from a pooled
+    sample cut the value axis into ``world`` ranges of about equal population, an all-to-all brings
+    range r to rank r, which sorts it and computes q = p m / rank with the ranks of the whole column
+    (it knows how many numbers lie above its range) and the running minimum inside the range; the
+    minimum over the ranges above arrives with one small all-gather; a second all-to-all takes the
+    q-values back to the rows they belong to.  Equal p-values always share a range."""
     world, rank = _world(group)
     C, n_local = cols.shape
     if world == 1:
         return torch.stack([bh(cols[c].contiguous()) for c in range(C)]) if C else cols.clone()
     device = cols.device
-    counts = _all_counts(n_local, device, group, world)
-    owned = [c for c in range(C) if c % world == rank]            # my columns
-    n_owned = [len(range(r, C, world)) for r in range(world)]     # columns owned by rank r
-    # send: for destination r, the columns it owns (each [n_local]), column after column
-    send = torch.cat([cols[c] for r in range(world) for c in range(r, C, world)]) if C else cols.reshape(0)
-    send_split = [n_owned[r] * n_local for r in range(world)]
-    recv_split = [len(owned) * counts[r] for r in range(world)]
-    recv = torch.empty(sum(recv_split), dtype=cols.dtype, device=device)
-    dist.all_to_all_single(recv, send.contiguous(), recv_split, send_split, group=group)
-    # recv: source rank after source rank, [len(owned), counts[r]] each -> whole columns
-    qback = torch.empty_like(recv)
-    if owned:
-        parts = torch.split(recv, recv_split)
-        qparts = [torch.empty_like(p).view(len(owned), -1) for p in parts]
-        for j in range(len(owned)):
-            whole = torch.cat([p.view(len(owned), -1)[j] for p in parts])
-            q = bh(whole)
-            for qp, piece in zip(qparts, torch.split(q, counts)):
-                qp[j] = piece
-        qback = torch.cat([qp.reshape(-1) for qp in qparts])
-    # reverse exchange: every rank gets the q-values of its own rows back, owner after owner
-    got = torch.empty(sum(send_split), dtype=cols.dtype, device=device)
-    dist.all_to_all_single(got, qback, send_split, recv_split, group=group)
-    out = torch.empty_like(cols)
-    for r, chunk in enumerate(torch.split(got, send_split)):
-        for j, c in enumerate(range(r, C, world)):
-            out[c] = chunk.view(n_owned[r], n_local)[j]
+    inf = float('inf')
+    out = torch.full_like(cols, float('nan'))
+    for c in range(C):
+        col = cols[c]
+        rows = torch.nonzero(col == col).squeeze(1)          # rows that hold a number
+        v = col[rows]
+        # splitters: FDR_SAMPLE numbers of every rank (evenly spaced rows; NaN where a rank has none)
+        if v.numel():
+            pick = torch.linspace(0, v.numel() - 1, FDR_SAMPLE, device=device).round().long()
+            mine = v[pick]
+        else:
+            mine = torch.full((FDR_SAMPLE,), float('nan'), dtype=cols.dtype, device=device)
+        pooled = torch.empty(world * FDR_SAMPLE, dtype=cols.dtype, device=device)
+        dist.all_gather_into_tensor(pooled, mine, group=group)
+        pooled = torch.sort(pooled[pooled == pooled]).values
+        if pooled.numel():
+            at = (torch.arange(1, world, device=device) * pooled.numel()) // world
+            splitters = pooled[at]
+        else:
+            splitters = torch.zeros(world - 1, dtype=cols.dtype, device=device)
+        # range of a value: the number of splitters below it (equal values: one range)
+        dest = torch.bucketize(v, splitters).to(torch.uint8 if world <= 256 else torch.int32)
+        order = torch.argsort(dest, stable=True)
+        send = v[order]
+        rows = rows[order]
+        counts = torch.bincount(dest.long(), minlength=world)
+        table = torch.empty((world, world), dtype=torch.int64, device=device)    # [source, range]
+        dist.all_gather_into_tensor(table.view(-1), counts, group=group)
+        table = table.cpu()
+        send_split = table[rank].tolist()
+        recv_split = table[:, rank].tolist()
+        per_range = table.sum(0)
+        total = int(per_range.sum())
+        if total == 0:
+            continue                                          # the same decision on every rank
+        above = int(per_range[rank + 1:].sum())
+        recv = torch.empty(sum(recv_split), dtype=cols.dtype, device=device)
+        dist.all_to_all_single(recv, send, recv_split, send_split, group=group)
+        q = bh(recv, above=above, total=total) if recv.numel() else recv
+        low = q.min().reshape(1) if q.numel() else torch.full((1,), inf, dtype=cols.dtype, device=device)
+        lows = torch.empty(world, dtype=cols.dtype, device=device)
+        dist.all_gather_into_tensor(lows, low, group=group)
+        if rank + 1 < world and q.numel():
+            q = torch.clamp(q, max=lows[rank + 1:].min())     # running minimum over the ranges above
+        back = torch.empty(sum(send_split), dtype=cols.dtype, device=device)
+        dist.all_to_all_single(back, q.contiguous(), send_split, recv_split, group=group)
+        out[c, rows] = back
     return out
 
 
@@ -163,7 +197,7 @@ def warm_up(device, bh=None, group=None):
         return
     cols = torch.rand((3, 4 + rank), dtype=torch.float64, device=device)
     keys = torch.arange(4 + rank, dtype=torch.int64, device=device) | (rank << 32)
-    fdr_columns(cols, bh or (lambda p: p.clone()), group=group)
+    fdr_columns(cols, bh or (lambda p, above=0, total=None: p.clone()), group=group)
     gather_columns(cols, keys, group=group)
     if device.type == 'cuda':
         torch.cuda.synchronize(device)

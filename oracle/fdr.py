@@ -27,6 +27,29 @@ def fdr_bh(p):
     return out
 
 
+def fdr_bh_segment(p, above=0, total=None):
+    """BH q-values of the numbers in ``p`` (NaNs skipped) when they are one value range of a column of
+    ``total`` numbers, ``above`` of them larger than all of ``p``: the running minimum stops at the
+    range's own largest value (the caller takes the minimum with the ranges above).  With the
+    defaults this is ``multipletests_filter_nan``."""
+    p = np.asarray(p, dtype=np.float64)
+    nans = np.isnan(p)
+    v = p[~nans]
+    m = v.size if total is None else int(total)
+    out = p.copy()
+    if v.size == 0:
+        return out
+    order = np.argsort(v, kind='stable')
+    ranks = m - above - np.arange(v.size - 1, -1, -1)          # ascending ranks of the sorted values
+    q = v[order] / (ranks / m)
+    q = np.minimum.accumulate(q[::-1])[::-1]
+    q = np.minimum(q, 1.0)
+    res = np.empty(v.size)
+    res[order] = q
+    out[~nans] = res
+    return out
+
+
 def multipletests_filter_nan(pvalues):
     pvalues = np.asarray(pvalues, dtype=np.float64)
     nans = np.isnan(pvalues)

@@ -56,7 +56,7 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     o.struct_size = 3
     h = C.c_void_p()
     assert lib.ncb_create(C.byref(h), 0, C.byref(o)) == L.NCB_ERR_INVALID
-    for field, value in (('em_fp64', 0), ('em_tol', float('nan')), ('reg_covar', -1.0), ('min_coverage', -1),
+    for field, value in (('em_tol', float('nan')), ('reg_covar', -1.0), ('min_coverage', -1),
                          ('em_max_iter', 0), ('n_samples', -1), ('depleted_condition', 2)):
         o = L.default_opts()
         setattr(o, field, value)

@@ -97,36 +97,64 @@ def _columns_of(rank, n_cols):
 
 
 def _fdr_worker(rank, world, port, out, n_cols):
-    from oracle.fdr import fdr_bh
+    from oracle.fdr import fdr_bh_segment
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    bh = lambda p: torch.from_numpy(fdr_bh(p.numpy()))      # noqa: E731  (the GPU tests use Engine.bh_fdr)
+    # (the GPU path passes Engine.bh_fdr)
+    bh = lambda p, above=0, total=None: torch.from_numpy(fdr_bh_segment(p.numpy(), above, total))      # noqa: E731
     warm_up(torch.device('cpu'), bh)
     q = fdr_columns(torch.from_numpy(_columns_of(rank, n_cols)), bh)
     torch.save(q, f'{out}.{rank}')
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n_cols', [1, 3, 5])
-def test_fdr_columns_gloo_world2_equals_the_correction_of_the_whole_table(tmp_path, n_cols):
-    """postprocessing.py:255-285 corrects a column over ALL result rows: sharded over two ranks the
-    q-values must be those of the concatenated column (oracle/fdr.py), whoever owns the column."""
-    from oracle.fdr import fdr_bh
+@pytest.mark.parametrize('world,n_cols', [(2, 1), (2, 3), (2, 5), (3, 2)])
+def test_fdr_columns_gloo_equals_the_correction_of_the_whole_table(tmp_path, world, n_cols):
+    """postprocessing.py:255-285 corrects a column over ALL result rows: sharded over the ranks the
+    q-values must be those of the concatenated column (oracle/fdr.py), NaNs skipped, however the
+    value ranges fall."""
+    from oracle.fdr import multipletests_filter_nan
     out = str(tmp_path / 'q.pt')
-    mp.spawn(_fdr_worker, args=(2, _free_port(), out, n_cols), nprocs=2, join=True)
-    whole = np.concatenate([_columns_of(0, n_cols), _columns_of(1, n_cols)], axis=1)
-    want = np.stack([fdr_bh(whole[c]) for c in range(n_cols)])
-    got = np.concatenate([torch.load(f'{out}.{r}').numpy() for r in range(2)], axis=1)
-    assert np.array_equal(np.isnan(got), np.isnan(want))
+    mp.spawn(_fdr_worker, args=(world, _free_port(), out, n_cols), nprocs=world, join=True)
+    whole = np.concatenate([_columns_of(r, n_cols) for r in range(world)], axis=1)
+    want = np.stack([multipletests_filter_nan(whole[c]) for c in range(n_cols)])
+    got = np.concatenate([torch.load(f'{out}.{r}').numpy() for r in range(world)], axis=1)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and not np.isnan(want).all()
+    assert np.allclose(got, want, rtol=1e-13, atol=0, equal_nan=True)
+
+
+def test_segment_correction_of_value_ranges_composes_to_the_whole_column():
+    """oracle.fdr.fdr_bh_segment (the contract of ncb_bh_fdr_segment): ranges corrected one by one with
+    the ranks of the whole column, then the minimum of the ranges above, give the whole-column q-values."""
+    from oracle.fdr import fdr_bh_segment, multipletests_filter_nan
+    rng = np.random.default_rng(5)
+    p = rng.random(500) ** 2
+    p[rng.random(500) < 0.1] = np.nan
+    p[:20] = p[20:40]
+    want = multipletests_filter_nan(p)
+    cuts = [0.0, 0.05, 0.3, 0.31, 2.0]
+    total = int((~np.isnan(p)).sum())
+    got = np.full(p.size, np.nan)
+    lows = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        sel = (p > lo) & (p <= hi) if lo > 0 else (p <= hi)
+        above = int((p > hi).sum())
+        q = fdr_bh_segment(p[sel], above, total)
+        got[sel] = q
+        lows.append((hi, np.nanmin(q) if q.size else np.inf))
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        sel = (p > lo) & (p <= hi) if lo > 0 else (p <= hi)
+        carry = min([m for h, m in lows if h > hi], default=np.inf)
+        got[sel] = np.minimum(got[sel], carry)
     assert np.allclose(got, want, rtol=1e-13, atol=0, equal_nan=True)
 
 
 def test_fdr_columns_single_process():
-    from oracle.fdr import fdr_bh
+    from oracle.fdr import fdr_bh_segment, multipletests_filter_nan
     cols = _columns_of(0, 3)
-    q = fdr_columns(torch.from_numpy(cols), lambda p: torch.from_numpy(fdr_bh(p.numpy())))
-    assert np.allclose(q.numpy(), np.stack([fdr_bh(c) for c in cols]), equal_nan=True)
+    q = fdr_columns(torch.from_numpy(cols), lambda p, above=0, total=None: torch.from_numpy(fdr_bh_segment(p.numpy(), above, total)))
+    assert np.allclose(q.numpy(), np.stack([multipletests_filter_nan(c) for c in cols]), equal_nan=True)
 
 
 def test_lpt_imbalance():
