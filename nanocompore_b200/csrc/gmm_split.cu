@@ -31,12 +31,30 @@
 // used.
 #include "gmm_common.cuh"
 
+#ifndef NCB_GS_U_INIT
+#define NCB_GS_U_INIT 4
+#endif
+#ifndef NCB_GS_INTSEL
+#define NCB_GS_INTSEL 1    /* EM kernel: comparisons of doubles on the integer pipe (e_step_one_i) */
+#endif
+
 namespace ncb {
 
 // record of a position: [0, 12) the parameters of both components as the E-step uses them
 // (CompE x 2), [12, 18) totals of the position (n, sum x, y, xx, xy, yy), 18 BIC of the K = 1 fit,
 // 19 which component the next pass sums (0 / 1), 20 EM passes done
 enum { REC_CE = 0, REC_TOT = 12, REC_BIC1 = 18, REC_SECOND = 19, REC_ITERS = 20 };
+
+// The positions a launch works on: the worklists of one or two size classes, taken as one sequence
+// (one launch for the classes of up to 128 and up to 256 reads: one tail instead of two).
+struct WorkLists {
+    const int32_t *list_a, *count_a, *list_b, *count_b;   // b may be absent (NULL)
+    __device__ __forceinline__ int total() const { return *count_a + (count_b ? *count_b : 0); }
+    __device__ __forceinline__ int32_t at(int i) const {
+        const int na = *count_a;
+        return i < na ? list_a[i] : list_b[i - na];
+    }
+};
 
 template <int SUB, int NV>
 __device__ __forceinline__ void sub_reduce_add(double (&v)[NV]) {
@@ -66,19 +84,25 @@ __device__ __forceinline__ int load_fit_reads(const NcbDeviceArgs &a, int64_t p,
         n_in = a.n_reads;
         zin = a.zbuf + p * (int64_t)n_in;
     }
+    // four loads per lane are in flight before the first is looked at: one round trip to HBM per
+    // 128 entries instead of one per 32
     int n = 0;
 #pragma unroll 1
-    for (int base = 0; base < n_in; base += 32) {
-        const int e = base + lane;
-        float2 z = make_float2(0.f, 0.f);
-        bool ok = false;
-        if (e < n_in) {
-            z = zin[e];
-            ok = z.x == z.x;
+    for (int base = 0; base < n_in; base += 128) {
+        float2 z[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = base + j * 32 + lane;
+            z[j] = make_float2(__int_as_float(0x7fc00000), 0.f);
+            if (e < n_in) z[j] = zin[e];
         }
-        const unsigned m = __ballot_sync(NCB_FULL, ok);
-        if (ok) val[n + __popc(m & ((1u << lane) - 1u))] = z;
-        n += __popc(m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool ok = z[j].x == z[j].x;
+            const unsigned m = __ballot_sync(NCB_FULL, ok);
+            if (ok) val[n + __popc(m & ((1u << lane) - 1u))] = z[j];
+            n += __popc(m);
+        }
     }
     return n;
 }
@@ -113,8 +137,9 @@ struct InitSmem {
 
 template <int SUB, int CAP, int WPC, int MINB>
 __global__ void __launch_bounds__(WPC * 32, MINB)
-gmm_init_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_t *fetch, double *rec) {
+gmm_init_kernel(NcbDeviceArgs a, WorkLists wl, int32_t *fetch, double *rec) {
     constexpr int G = 32 / SUB;
+    constexpr int UI = NCB_GS_U_INIT;   // trips of a pass over the reads unrolled together
     extern __shared__ __align__(16) unsigned char smem[];
     typedef InitSmem<SUB, CAP> Smem;
     Smem *sm = reinterpret_cast<Smem *>(smem) + (threadIdx.x >> 5);
@@ -122,7 +147,7 @@ gmm_init_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int3
     const int sub = lane & (SUB - 1), grp = lane / SUB;
     const float2 *val = sm->val[grp];
     uint8_t *k0 = sm->k0[grp];
-    const int total = *count;
+    const int total = wl.total();
     const double reg = a.reg_covar;
     for (;;) {
         int i0 = 0;
@@ -134,7 +159,7 @@ gmm_init_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int3
 #pragma unroll 1
         for (int gi = 0; gi < G; ++gi) {
             const int idx = i0 + gi;
-            const int64_t q = idx < total ? (int64_t)list[idx] : -1;
+            const int64_t q = idx < total ? (int64_t)wl.at(idx) : -1;
             int nq = 0;
             if (q >= 0 && (unsigned)a.gmm_n[q] >= 2u) nq = load_fit_reads(a, q, sm->val[gi], lane);
             if (grp == gi) { p = q; n = nq; }
@@ -146,7 +171,7 @@ gmm_init_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int3
 
         // K = 1: closed form
         double T[5] = {0, 0, 0, 0, 0};   // sum x, y, xx, xy, yy
-#pragma unroll 1
+#pragma unroll UI
         for (int e = sub; e < n; e += SUB) {
             const float2 zf = val[e];
             const double x = (double)zf.x, y = (double)zf.y;
@@ -178,7 +203,7 @@ gmm_init_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int3
             for (int pass = 0; pass < 2; ++pass) {
                 double best = -1.0;
                 int beste = 0x7fffffff;
-#pragma unroll 1
+#pragma unroll UI
                 for (int e = sub; e < n; e += SUB) {
                     const float2 zf = val[e];
                     const double dx = (double)zf.x - refx, dy = (double)zf.y - refy;
@@ -207,7 +232,7 @@ gmm_init_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int3
             if (__all_sync(NCB_FULL, done)) break;
             double k[4] = {0, 0, 0, 0};   // n0, sx0, sy0, changed
             if (!done) {
-#pragma unroll 1
+#pragma unroll UI
                 for (int e = sub; e < n; e += SUB) {
                     const float2 zf = val[e];
                     const double x = (double)zf.x, y = (double)zf.y;
@@ -246,7 +271,7 @@ gmm_init_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int3
         double r7[7] = {0, 0, 0, 0, 0, 0, 0};
         {
             double acc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 1
+#pragma unroll UI
             for (int e = sub; e < n; e += SUB) {
                 const float2 zf = val[e];
                 accumulate6(acc, k0[e] ? 1.0 : 0.0, (double)zf.x, (double)zf.y);
@@ -294,9 +319,9 @@ __device__ __forceinline__ double widen01(float r) {
     return __hiloint2double(tiny ? 0 : (int)hi, tiny ? 0 : (int)lo);
 }
 
-template <int SUB, int CAP, int WPC, int MINB, bool F32>
+template <int SUB, int CAP, int WPC, int MINB, bool F32, int U>
 __global__ void __launch_bounds__(WPC * 32, MINB)
-gmm_em_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_t *fetch, double *rec) {
+gmm_em_kernel(NcbDeviceArgs a, WorkLists wl, int32_t *fetch, double *rec) {
     constexpr int G = 32 / SUB;
     extern __shared__ __align__(16) unsigned char smem[];
     typedef EmSmem<SUB, CAP> Smem;
@@ -305,14 +330,14 @@ gmm_em_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_
     const int sub = lane & (SUB - 1), grp = lane / SUB;
     const float2 *val = sm->val[grp];
     const double *tot = sm->tot[grp];
-    const int total = *count;
+    const int total = wl.total();
     const int64_t P = a.n_positions;
     const double reg = a.reg_covar;
     // state of this group's position
     bool have = false, second = false;
     int64_t p = -1;
     int n = 0, it = 0;
-    double prev = 0.0, dn = 1.0;
+    double prev = 0.0, dn = 1.0, rdn = 1.0;   // rdn = 1 / dn, correctly rounded
     CompE ce[2];
     ce[0].mx = ce[0].my = ce[0].ha = ce[0].hb = ce[0].hc = ce[0].cst = 0.0;   // a group without a position
     ce[1] = ce[0];                                                            // computes and discards
@@ -330,7 +355,7 @@ gmm_em_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_
                     if (lane == 0) idx = atomicAdd(fetch, 1);
                     idx = __shfl_sync(NCB_FULL, idx, 0);
                     if (idx >= total) { exhausted = true; break; }
-                    const int64_t c = (int64_t)list[idx];
+                    const int64_t c = (int64_t)wl.at(idx);
                     if ((unsigned)a.gmm_n[c] >= 2u && rec[c * NCB_GMM_REC + REC_TOT] >= 2.0) { q = c; break; }
                 }
                 if (q < 0) break;
@@ -342,6 +367,7 @@ gmm_em_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_
                     load_ce(r + REC_CE, ce);
                     second = r[REC_SECOND] != 0.0;
                     dn = r[REC_TOT];
+                    rdn = __drcp_rn(dn);
                     for (int i = sub; i < 6; i += SUB) sm->tot[gi][i] = r[REC_TOT + i];
                 }
             }
@@ -357,29 +383,61 @@ gmm_em_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_
             double acc[6] = {0, 0, 0, 0, 0, 0};
             double ll = 0.0;
             const int nn = have ? n : 0;
+            // U reads of a lane go through the chain at a time (independent instructions to fill the
+            // latency of the dependent ones); the last trip may hold fewer: the missing ones are
+            // computed on the lane's first read of the trip and enter every sum with weight zero
             if (F32) {
                 const CompEf c0 = narrow(ce[0]), c1 = narrow(ce[1]);
                 float lmax_sum = 0.f, lprod = 1.f;
 #pragma unroll 1
-                for (int e = sub; e < nn; e += SUB) {
-                    const float2 zf = val[e];
-                    const RespF r = e_step_f(c0, c1, zf.x, zf.y);
-                    lmax_sum += r.lmax;
-                    lprod *= r.sum;
-                    accumulate6(acc, widen01(second ? r.r1 : r.r0), (double)zf.x, (double)zf.y);
+                for (int e = sub; e < nn; e += U * SUB) {
+                    float2 zf[U];
+                    bool ok[U];
+                    RespF r[U];
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        ok[j] = j == 0 || e + j * SUB < nn;
+                        zf[j] = val[ok[j] ? e + j * SUB : e];
+                    }
+#pragma unroll
+                    for (int j = 0; j < U; ++j) r[j] = e_step_f(c0, c1, zf[j].x, zf[j].y);
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        lmax_sum += ok[j] ? r[j].lmax : 0.f;
+                        lprod *= ok[j] ? r[j].sum : 1.f;
+                        const float w = second ? r[j].r1 : r[j].r0;
+                        accumulate6(acc, widen01(ok[j] ? w : 0.f), (double)zf[j].x, (double)zf[j].y);
+                    }
                 }
                 ll = (double)lmax_sum + (double)__logf(lprod);
             } else {
                 const CompE c0 = ce[0], c1 = ce[1];
                 double lprod = 1.0;
 #pragma unroll 1
-                for (int e = sub; e < nn; e += SUB) {
-                    const float2 zf = val[e];
-                    const double x = (double)zf.x, y = (double)zf.y;
-                    const RespOne r = e_step_one(c0, c1, x, y, second);
-                    ll += r.lmax;
-                    lprod *= r.sum;
-                    accumulate6(acc, r.r, x, y);
+                for (int e = sub; e < nn; e += U * SUB) {
+                    double x[U], y[U];
+                    bool ok[U];
+                    RespOne r[U];
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        ok[j] = j == 0 || e + j * SUB < nn;
+                        const float2 zf = val[ok[j] ? e + j * SUB : e];
+                        x[j] = (double)zf.x; y[j] = (double)zf.y;
+                    }
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+#if NCB_GS_INTSEL
+                        r[j] = e_step_one_i(c0, c1, x[j], y[j], second ? 0x80000000u : 0u);
+#else
+                        r[j] = e_step_one(c0, c1, x[j], y[j], second);
+#endif
+                    }
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        ll += ok[j] ? r[j].lmax : 0.0;
+                        lprod *= ok[j] ? r[j].sum : 1.0;
+                        accumulate6(acc, ok[j] ? r[j].r : 0.0, x[j], y[j]);
+                    }
                 }
                 ll += log(lprod);
             }
@@ -392,7 +450,7 @@ gmm_em_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_
         double s[12];
         derive12(r7, tot, second, s);
         ++it;
-        const double Lm = r7[6] / dn;
+        const double Lm = r7[6] * rdn;    // mean log-likelihood (a division: 15 instructions on every lane)
         const bool last = fabs(Lm - prev) < a.em_tol || it >= a.em_max_iter;
         prev = Lm;
         if (have && last && a.diag_f64 && sub == 0) {
@@ -425,13 +483,13 @@ gmm_em_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_
 // ---- final E-step and what follows the fit -----------------------------------------------------
 template <int SUB, int WPC, int MINB, bool F32>
 __global__ void __launch_bounds__(WPC * 32, MINB)
-gmm_final_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int32_t *fetch, const double *rec) {
+gmm_final_kernel(NcbDeviceArgs a, WorkLists wl, int32_t *fetch, const double *rec) {
     constexpr int G = 32 / SUB;
     extern __shared__ __align__(16) unsigned char smem[];
     PosShared *ps = reinterpret_cast<PosShared *>(smem) + (threadIdx.x >> 5) * G + (threadIdx.x & 31) / SUB;
     const int lane = threadIdx.x & 31;
     const int sub = lane & (SUB - 1), grp = lane / SUB;
-    const int total = *count;
+    const int total = wl.total();
     const int64_t P = a.n_positions;
     const bool soft = a.cluster_counts == NCB_COUNTS_SOFT;
     const int S2 = a.n_samples * 2;
@@ -441,7 +499,7 @@ gmm_final_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int
         i0 = __shfl_sync(NCB_FULL, i0, 0);
         if (i0 >= total) break;
         const int idx = i0 + grp;
-        int64_t p = idx < total ? (int64_t)list[idx] : -1;
+        int64_t p = idx < total ? (int64_t)wl.at(idx) : -1;
         const double *r = rec + (p < 0 ? 0 : p) * NCB_GMM_REC;
         if (p >= 0 && !((unsigned)a.gmm_n[p] >= 2u && r[REC_TOT] >= 2.0)) p = -1;
         for (int i = sub; i < S2; i += SUB) { ps->scnt[i] = 0u; ps->sacc[i] = 0.0; }
@@ -469,11 +527,23 @@ gmm_final_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int
             const CompE c0 = ce[0], c1 = ce[1];
             const CompEf c0f = narrow(ce[0]), c1f = narrow(ce[1]);
             double lprod = 1.0;
+            // four reads per lane are loaded before the first is used (one round trip to HBM per 4 SUB reads)
 #pragma unroll 1
-            for (int e = sub; e < n_in; e += SUB) {
-                const float2 zf = zin[e];
+            for (int base = 0; base < n_in; base += 4 * SUB) {
+                float2 z4[4];
+                uint32_t f4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = base + j * SUB + sub;
+                    z4[j] = make_float2(__int_as_float(0x7fc00000), 0.f);
+                    f4[j] = 0u;
+                    if (e < n_in) { z4[j] = zin[e]; f4[j] = (uint32_t)__ldg(lab + e) & 0x7fu; }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                const float2 zf = z4[j];
                 if (!(zf.x == zf.x)) continue;
-                const uint32_t f = (uint32_t)__ldg(lab + e) & 0x7fu;
+                const uint32_t f = f4[j];
                 Resp rr;
                 if (F32) {
                     const RespF rf = e_step_f(c0f, c1f, zf.x, zf.y);
@@ -498,6 +568,7 @@ gmm_final_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int
                         atomicAdd(&ps->sacc[smp * 2 + 1], q1);
                     }
                 }
+            }
             }
             ll += log(lprod);
         }
@@ -527,33 +598,41 @@ gmm_final_kernel(NcbDeviceArgs a, const int32_t *list, const int32_t *count, int
 using namespace ncb;
 
 // lanes per position / warps per CTA / CTAs per SM of the three warp size classes
-#ifndef NCB_GS_SUB0
-#define NCB_GS_SUB0 8
-#endif
 #ifndef NCB_GS_SUB1
 #define NCB_GS_SUB1 8
 #endif
 #ifndef NCB_GS_SUB2
 #define NCB_GS_SUB2 16
 #endif
+// warps per CTA and CTAs per SM of the three kernels; reads a lane carries through the E-step at a time
 #ifndef NCB_GS_WPC
 #define NCB_GS_WPC 8
 #endif
-#ifndef NCB_GS_MINB
-#define NCB_GS_MINB 3
+#ifndef NCB_GS_MINB_INIT
+#define NCB_GS_MINB_INIT 3
+#endif
+#ifndef NCB_GS_MINB_EM
+#define NCB_GS_MINB_EM 2      /* 117 registers at U = 3 */
+#endif
+#ifndef NCB_GS_MINB_FINAL
+#define NCB_GS_MINB_FINAL 3
+#endif
+#ifndef NCB_GS_U_EM
+#define NCB_GS_U_EM 3         /* measured per 100 k positions of config 3: 1.244 ms (U = 1, 3 CTAs) / 1.209 (2, 2) / 1.207 (3, 2) */
 #endif
 
 template <int SUB, int CAP, bool F32>
-static int split_class(const NcbDeviceArgs &a, const int32_t *list, const int32_t *count, int32_t *f_init,
-                       int32_t *f_em, int32_t *f_final, int sm_count, cudaStream_t s, bool configure) {
-    constexpr int WPC = NCB_GS_WPC, MINB = NCB_GS_MINB, G = 32 / SUB;
+static int split_class(const NcbDeviceArgs &a, const WorkLists &wl, int32_t *f_init, int32_t *f_em, int32_t *f_final,
+                       int sm_count, cudaStream_t s, bool configure) {
+    constexpr int WPC = NCB_GS_WPC, G = 32 / SUB;
+    constexpr int MB_I = NCB_GS_MINB_INIT, MB_E = NCB_GS_MINB_EM, MB_F = NCB_GS_MINB_FINAL;
     constexpr size_t sm_init = WPC * sizeof(InitSmem<SUB, CAP>), sm_em = WPC * sizeof(EmSmem<SUB, CAP>),
                      sm_final = WPC * G * sizeof(PosShared);
-    static_assert(sm_init * MINB + 1024 * MINB <= 233472 && sm_em * MINB + 1024 * MINB <= 233472,
+    static_assert(sm_init * MB_I + 1024 * MB_I <= 233472 && sm_em * MB_E + 1024 * MB_E <= 233472,
                   "split mixture kernels: the CTAs of an SM do not fit its shared memory");
-    auto k_init = gmm_init_kernel<SUB, CAP, WPC, MINB>;
-    auto k_em = gmm_em_kernel<SUB, CAP, WPC, MINB, F32>;
-    auto k_final = gmm_final_kernel<SUB, WPC, MINB, F32>;
+    auto k_init = gmm_init_kernel<SUB, CAP, WPC, MB_I>;
+    auto k_em = gmm_em_kernel<SUB, CAP, WPC, MB_E, F32, NCB_GS_U_EM>;
+    auto k_final = gmm_final_kernel<SUB, WPC, MB_F, F32>;
     if (configure) {
         if (cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_init) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(k_em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_em) != cudaSuccess) return -1;
@@ -561,38 +640,48 @@ static int split_class(const NcbDeviceArgs &a, const int32_t *list, const int32_
         return 0;
     }
     const int64_t P = a.n_positions;
-    const int64_t need = (P + WPC * G - 1) / (WPC * G), cap = (int64_t)sm_count * MINB;
-    const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-    k_init<<<grid, WPC * 32, sm_init, s>>>(a, list, count, f_init, a.gmm_rec);
-    k_em<<<grid, WPC * 32, sm_em, s>>>(a, list, count, f_em, a.gmm_rec);
-    k_final<<<grid, WPC * 32, sm_final, s>>>(a, list, count, f_final, a.gmm_rec);
+    const int64_t need = (P + WPC * G - 1) / (WPC * G);
+    auto grid = [&](int minb) {
+        const int64_t cap = (int64_t)sm_count * minb;
+        return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+    };
+    k_init<<<grid(MB_I), WPC * 32, sm_init, s>>>(a, wl, f_init, a.gmm_rec);
+    k_em<<<grid(MB_E), WPC * 32, sm_em, s>>>(a, wl, f_em, a.gmm_rec);
+    k_final<<<grid(MB_F), WPC * 32, sm_final, s>>>(a, wl, f_final, a.gmm_rec);
     return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
 
+// `wide`: the class of up to 512 reads (16 lanes per position); else the classes of up to 128 and up to
+// 256 reads as one launch (8 lanes per position).  The work counters are those of the larger class.
 template <bool F32>
-static int split_all(const NcbDeviceArgs &a, const NcbWorklists &w, int cls, int sm_count, cudaStream_t s, bool configure) {
+static int split_all(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s, bool configure) {
     const int64_t P = a.n_positions;
-    const int32_t *list = configure ? nullptr : w.class_list + (int64_t)cls * P;
-    const int32_t *count = configure ? nullptr : w.class_count + cls;
-    int32_t *f_init = configure ? nullptr : w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM) + cls;
-    int32_t *f_em = configure ? nullptr : w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM_EM) + cls;
-    int32_t *f_final = configure ? nullptr : w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM_FINAL) + cls;
-    switch (cls) {
-    case 0: return split_class<NCB_GS_SUB0, 128, F32>(a, list, count, f_init, f_em, f_final, sm_count, s, configure);
-    case 1: return split_class<NCB_GS_SUB1, 256, F32>(a, list, count, f_init, f_em, f_final, sm_count, s, configure);
-    case 2: return split_class<NCB_GS_SUB2, 512, F32>(a, list, count, f_init, f_em, f_final, sm_count, s, configure);
+    const int cls = wide ? 2 : 1;
+    WorkLists wl{};
+    int32_t *f_init = nullptr, *f_em = nullptr, *f_final = nullptr;
+    if (!configure) {
+        wl.list_a = w.class_list + (int64_t)cls * P;
+        wl.count_a = w.class_count + cls;
+        if (!wide) {
+            wl.list_b = w.class_list;
+            wl.count_b = w.class_count;
+        }
+        f_init = w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM) + cls;
+        f_em = w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM_EM) + cls;
+        f_final = w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM_FINAL) + cls;
     }
-    return -1;
+    return wide ? split_class<NCB_GS_SUB2, 512, F32>(a, wl, f_init, f_em, f_final, sm_count, s, configure)
+                : split_class<NCB_GS_SUB1, 256, F32>(a, wl, f_init, f_em, f_final, sm_count, s, configure);
 }
 
 int ncb_configure_gmm_split(void) {
     NcbDeviceArgs a{};
     NcbWorklists w{};
-    for (int c = 0; c < 3; ++c)
-        if (split_all<false>(a, w, c, 0, 0, true) != 0 || split_all<true>(a, w, c, 0, 0, true) != 0) return -1;
+    for (int wide = 0; wide < 2; ++wide)
+        if (split_all<false>(a, w, wide != 0, 0, 0, true) != 0 || split_all<true>(a, w, wide != 0, 0, 0, true) != 0) return -1;
     return 0;
 }
 
-int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, int cls, int sm_count, cudaStream_t s) {
-    return a.em_fp32 ? split_all<true>(a, w, cls, sm_count, s, false) : split_all<false>(a, w, cls, sm_count, s, false);
+int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s) {
+    return a.em_fp32 ? split_all<true>(a, w, wide, sm_count, s, false) : split_all<false>(a, w, wide, sm_count, s, false);
 }

@@ -129,6 +129,7 @@ int ncb_launch_context(int64_t n_tx, int64_t n_rows, int64_t track_total, int32_
                        const double *pvalues, double *tracks, double *combined, int32_t *status,
                        int32_t context, const double *weights, cudaStream_t s);
 int ncb_configure_kernels(void);  // cudaFuncSetAttribute for large dynamic shared memory
-// mixture fit of warp size class `cls` (0..2) as three kernels (gmm_split.cu); returns the number launched
+// mixture fit of the warp size classes as three kernels (gmm_split.cu): classes 0 and 1 in one launch of
+// each, class 2 (`wide`) in its own; returns the number launched
 int ncb_configure_gmm_split(void);
-int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, int cls, int sm_count, cudaStream_t s);
+int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s);
