@@ -18,6 +18,7 @@ struct DevBuf {
 struct ncb_handle {
     int device = 0;
     int sm_count = 148;
+    bool sort32 = true;      // int16 batches: 32-bit sort keys in the warp classes (NCB_SORT32=0: 64-bit keys, for A/B runs)
     bool gmm_split = true;   // warp size classes: the three-kernel mixture fit (NCB_GMM_SPLIT=0: the fused kernel, for A/B runs)
     ncb_opts opts;
     std::string err;
@@ -198,6 +199,8 @@ int ncb_create(ncb_handle **out, int device, const ncb_opts *opts) {
         return NCB_ERR_CUDA;
     }
     *h->flag_host = 0;
+    const char *s32 = getenv("NCB_SORT32");
+    if (s32 && s32[0] == '0') h->sort32 = false;
     const char *gs = getenv("NCB_GMM_SPLIT");
     if (gs && gs[0] == '0') h->gmm_split = false;
     const char *t = getenv("NCB_TIMING");
@@ -291,6 +294,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     a.max_entries = b->n_reads > 0 ? b->n_reads : 0;
     a.n_vars = n_vars;
     a.signal_i16 = i16 ? 1 : 0;
+    a.sort32 = (i16 && n_vars == 2 && h->sort32) ? 1 : 0;
     a.error_flag = h->flag_dev;
     a.tests = o.tests;
     a.n_samples = S;

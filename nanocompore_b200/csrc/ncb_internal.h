@@ -15,6 +15,7 @@ struct NcbDeviceArgs {
     int32_t n_vars;              // floats per entry (2 for CSR, V for dense)
     int32_t max_entries;         // upper bound on the entries of a position (dense: R), 0 = unknown
     int32_t signal_i16;          // 1: `signal` holds int16 codes (NCB_LAYOUT_CSR_I16), value = (float)code
+    int32_t sort32;              // 1: the warp classes of an int16 batch sort 32-bit keys (NCB_SORT32=0: A/B runs)
     int32_t *error_flag;         // mapped host word: NCB_POS_TOO_MANY_READS is OR-ed in when a position is rejected
     // options
     int32_t tests;
