@@ -60,7 +60,9 @@ __device__ __forceinline__ KsProblem make_problem(int n0, int n1, long long h) {
     KsProblem q;
     q.m = max(n0, n1);
     q.n = min(n0, n1);
-    long long g = gcd_ll(n0, n1);
+    unsigned ga = (unsigned)q.m, gb = (unsigned)q.n;   // sample sizes fit 32 bits: no 64-bit remainders
+    while (gb) { const unsigned t = ga % gb; ga = gb; gb = t; }
+    const int g = (int)max(ga, 1u);
     q.mg = q.m / g;
     q.ng = q.n / g;
     q.h = h;
@@ -116,11 +118,16 @@ __global__ void ks_classify_kernel(int64_t nprob, const int32_t *n0, const int32
                     kind = NCB_KS_KIND_SMALL;
                 else if (k.n + 1 <= NCB_KS_RING_SMALL || span <= (double)NCB_KS_RING_SMALL) kind = NCB_KS_KIND_LARGE;
                 else kind = NCB_KS_KIND_HUGE;
-                bin = kind * NCB_KS_BUCKETS + cost_bucket((double)k.m * width);
+                // thread-per-problem kind: ordered by window (widest first), so that the problems of a
+                // block fit the same number of slots and the threads of a warp walk rows of like length
+                bin = kind * NCB_KS_BUCKETS + (kind == NCB_KS_KIND_SMALL ? NCB_KS_SMALL_WINDOW - 1 - (int)lenA
+                                                                         : cost_bucket((double)k.m * width));
             }
         }
         w.bin[q] = (uint8_t)bin;
-        if (bin != 255) atomicAdd(&w.hist[bin], 1);
+        // one atomic per (warp, bin): the problems of a batch fall into a handful of bins
+        const unsigned peers = __match_any_sync(__activemask(), bin);
+        if (bin != 255 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&w.hist[bin], __popc(peers));
     }
 }
 
@@ -168,9 +175,13 @@ __global__ void ks_scatter_kernel(int64_t nprob, NcbKsWork w) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nprob;
          q += (int64_t)gridDim.x * blockDim.x) {
         int bin = w.bin[q];
+        const unsigned peers = __match_any_sync(__activemask(), bin);
         if (bin != 255) {
-            int pos = atomicAdd(&w.cursor[bin], 1);
-            w.list[pos] = (int32_t)q;
+            const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&w.cursor[bin], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            w.list[base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)q;
         }
     }
 }
@@ -187,21 +198,32 @@ __device__ __forceinline__ double div_by_recip(double a, double b, double r) {
 
 // ---- thread per problem: unequal sizes, small window ------------------------------------
 #define KS_SMALL_THREADS 128
+// WINDOW slots of shared memory per problem.  Most problems of a batch at ordinary coverage have a
+// band of fewer than 32 columns (under the null D n ~ 15 at 100 reads per condition): a block whose
+// problems all fit 32 slots runs in the 32-slot instance, of which an SM holds twice as many (the
+// kernel waits on its dependent chain of five fp64 operations per cell: residency is throughput).
+// Both instances are launched over all blocks; a block leaves the one that is not its own.
+template <int WINDOW>
 __global__ void __launch_bounds__(KS_SMALL_THREADS)
 ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *p_out,
                 NcbKsWork w) {
-    extern __shared__ double A_all[];   // [NCB_KS_SMALL_WINDOW][KS_SMALL_THREADS] + reciprocals
-    double *rtab = A_all + NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS;
+    extern __shared__ double A_all[];   // [WINDOW][KS_SMALL_THREADS]
+    const double *__restrict__ rtab = w.rtab;    // reciprocals of the integers (per handle, L1 resident)
     const int lo = w.hist[NCB_KS_KIND_SMALL * NCB_KS_BUCKETS];
     const int hi = w.hist[(NCB_KS_KIND_SMALL + 1) * NCB_KS_BUCKETS];
     if (lo + (int)blockIdx.x * KS_SMALL_THREADS >= hi) return;   // whole block idle
-    for (int b = threadIdx.x; b < KS_RECIP_TABLE + 8; b += KS_SMALL_THREADS)   // + 8: prefetch slack
-        rtab[b] = b ? __drcp_rn((double)b) : 0.0;
-    __syncthreads();
     const int idx = lo + blockIdx.x * KS_SMALL_THREADS + threadIdx.x;
-    if (idx >= hi) return;
-    const int q = w.list[idx];
-    const KsProblem k = make_problem(n0[q], n1[q], h[q]);
+    const bool live = idx < hi;
+    const int q = live ? w.list[idx] : 0;
+    KsProblem k = make_problem(1, 2, 1);
+    bool wide = false;
+    if (live) {
+        k = make_problem(n0[q], n1[q], h[q]);
+        const long long maxj0 = min(ceildiv_ll(k.h, k.mg), (long long)k.n + 1);
+        wide = min(2 * maxj0 + 2, (long long)k.n + 1) >= 32;      // lenA of the classification
+    }
+    const bool block_wide = __syncthreads_or(wide) != 0;
+    if (block_wide != (WINDOW == NCB_KS_SMALL_WINDOW) || !live) return;
     double *A = A_all + threadIdx.x;
 #define AT(j) A[(j) * KS_SMALL_THREADS]
     const int n = k.n, m = k.m;
@@ -209,7 +231,7 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
     const int mg = (int)k.mg, ng = (int)k.ng, hh = (int)k.h;
     int minj = 0, maxj = min((hh + mg - 1) / mg, n + 1);
     int curlen = maxj - minj;
-    for (int j = 0; j < NCB_KS_SMALL_WINDOW; ++j) AT(j) = (j < maxj) ? 0.0 : 1.0;
+    for (int j = 0; j < WINDOW; ++j) AT(j) = (j < maxj) ? 0.0 : 1.0;
     // band of row i: minj = floor((ng i - h) / mg) + 1 and maxj = ceil((ng i + h) / mg), clamped.
     // Both numerators grow by ng <= mg per row, so the quotients advance by 0 or 1: they are
     // carried as (quotient, remainder) pairs -- no division in the row loop.
@@ -232,15 +254,15 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
         double dj = (double)minj;
         const double *rt = rtab + i + minj;
         // the cell above and the reciprocal of the next column are fetched before this column's
-        // store (they never alias it: src > jj), so shared-memory latency stays off the
+        // store (they never alias it: src > jj), so memory latency stays off the
         // loop-carried chain val -> val
         // (src <= len + 1 < window: see the classification; slots right of the band hold 1.0)
         double up = AT(shift);
-        double r = rt[0];
+        double r = __ldg(rt);
         for (int jj = 0; jj < len; ++jj) {
             const int src = jj + 1 + shift;
             const double up_next = AT(src);
-            const double r_next = rt[jj + 1];
+            const double r_next = __ldg(rt + jj + 1);
             const double num = NCB_DADD(NCB_DMUL(up, di), NCB_DMUL(val, dj));
             val = div_by_recip(num, di + dj, r);
             AT(jj) = val;
@@ -694,11 +716,11 @@ static const int KS_WAVE_WARPS = 8;
 static constexpr size_t KS_WAVE_SMEM_CTA = (NCB_KS_RING_FULL + 2 * KS_WAVE_WARPS * 32) * sizeof(double);
 static constexpr size_t KS_WAVE_SMEM_WARP = (size_t)KS_WAVE_WARPS * NCB_KS_RING_SMALL * sizeof(double);
 static constexpr size_t KS_WAVE_SMEM = KS_WAVE_SMEM_CTA > KS_WAVE_SMEM_WARP ? KS_WAVE_SMEM_CTA : KS_WAVE_SMEM_WARP;
-static const size_t KS_SMALL_SMEM = (NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS + KS_RECIP_TABLE + 8) * sizeof(double);
+static const size_t KS_SMALL_SMEM = (size_t)NCB_KS_SMALL_WINDOW * KS_SMALL_THREADS * sizeof(double);
 
 int ncb_configure_ks_kernels(void) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(ks_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMALL_SMEM);
+    e = cudaFuncSetAttribute(ks_small_kernel<NCB_KS_SMALL_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMALL_SMEM);
     if (e != cudaSuccess) return -1;
     e = cudaFuncSetAttribute(ks_wave_kernel<KS_WAVE_WARPS, NCB_KS_RING_SMALL>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_WAVE_SMEM);
@@ -724,7 +746,8 @@ int ncb_launch_ks_pvalues(int64_t nprob, const int32_t *n0, const int32_t *n1, c
     ks_wave_kernel<KS_WAVE_WARPS, NCB_KS_RING_SMALL>
         <<<sm_count * 3, KS_WAVE_WARPS * 32, KS_WAVE_SMEM, s>>>(n0, n1, h, p_out, w);
     int tblocks = (int)((nprob + KS_SMALL_THREADS - 1) / KS_SMALL_THREADS);
-    ks_small_kernel<<<tblocks, KS_SMALL_THREADS, KS_SMALL_SMEM, s>>>(n0, n1, h, p_out, w);
+    ks_small_kernel<NCB_KS_SMALL_WINDOW><<<tblocks, KS_SMALL_THREADS, KS_SMALL_SMEM, s>>>(n0, n1, h, p_out, w);
+    ks_small_kernel<32><<<tblocks, KS_SMALL_THREADS, KS_SMALL_SMEM / (NCB_KS_SMALL_WINDOW / 32), s>>>(n0, n1, h, p_out, w);
     ks_equal_kernel<<<tblocks, KS_SMALL_THREADS, 0, s>>>(n0, h, p_out, w);
-    return cudaGetLastError() == cudaSuccess ? 6 : -1;
+    return cudaGetLastError() == cudaSuccess ? 7 : -1;
 }
