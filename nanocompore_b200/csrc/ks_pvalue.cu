@@ -49,6 +49,9 @@ __device__ __forceinline__ long long ceildiv_ll(long long a, long long b) {   //
 #ifndef KS_USE_STRIP
 #define KS_USE_STRIP 1    /* 0: narrow bands stay on the chunked warp form (A/B builds) */
 #endif
+#ifndef KS_SMALL_TWO_ROWS
+#define KS_SMALL_TWO_ROWS 1   /* thread-per-problem kernel: two rows per trip (0: one, for A/B builds) */
+#endif
 #define KS_SMALL_MAX_CELLS 16384.0   /* band cells a single thread may walk (~0.4 ms) */
 
 struct KsProblem {
@@ -238,7 +241,82 @@ ks_small_kernel(const int32_t *n0, const int32_t *n1, const int64_t *h, double *
     int q_lo = -((hh + mg - 1) / mg), r_lo = q_lo * -mg - hh;          // floor(-h / mg), remainder in [0, mg)
     int q_hi = (hh + mg - 1) / mg, r_hi = (hh + mg - 1) - q_hi * mg;   // floor((h + mg - 1) / mg)
     double result = -1.0;
-    for (int i = 1; i <= m; ++i) {
+    int i = 1;
+#if KS_SMALL_TWO_ROWS
+    // Two rows per trip.  Row b = i + 1 runs one column behind row a = i: the cell above b's is a's
+    // cell of the step before (a register), so the two cells of a step are independent -- two
+    // dependent chains of five fp64 operations in flight per thread instead of one, which is what this
+    // latency-bound kernel lacks (its residency is fixed by the windows in shared memory) -- and they
+    // share i + j, its reciprocal and the loop.  Only row b is stored.  Same cells, same operations
+    // per cell: the bits of the one-row form.
+    for (; i + 1 <= m; i += 2) {
+        const int minj_p = minj, len_p = curlen;
+        r_lo += ng;
+        if (r_lo >= mg) { r_lo -= mg; ++q_lo; }
+        r_hi += ng;
+        if (r_hi >= mg) { r_hi -= mg; ++q_hi; }
+        const int minj_a = min(max(q_lo + 1, 0), n), maxj_a = min(q_hi, n + 1);
+        if (maxj_a <= minj_a) { result = 1.0; break; }
+        r_lo += ng;
+        if (r_lo >= mg) { r_lo -= mg; ++q_lo; }
+        r_hi += ng;
+        if (r_hi >= mg) { r_hi -= mg; ++q_hi; }
+        const int minj_b = min(max(q_lo + 1, 0), n), maxj_b = min(q_hi, n + 1);
+        minj = minj_b; maxj = maxj_b;
+        if (maxj_b <= minj_b) { result = 1.0; break; }
+        const int len_a = maxj_a - minj_a, len_b = maxj_b - minj_b, da = minj_b - minj_a;
+        const double dia = (double)i, dib = dia + 1.0;
+        double va = (minj_a == 0) ? 0.0 : 1.0, vb = (minj_b == 0) ? 0.0 : 1.0;
+        double dja = (double)minj_a, djb = (double)minj_b;
+        double a_col = 1.0;                  // row a at the column row b computes next (1 right of a's band)
+        const double *rt = rtab + i + minj_a;
+        const int shift = minj_a - minj_p;
+        double up = AT(shift);
+        double r = __ldg(rt);
+        int t = 0;
+        // row a alone: the columns row b does not start at
+        const int t1 = min(da + 1, len_a);
+        for (; t < t1; ++t) {
+            const double up_next = AT(shift + t + 1);
+            const double r_next = __ldg(rt + t + 1);
+            va = div_by_recip(NCB_DADD(NCB_DMUL(up, dia), NCB_DMUL(va, dja)), dia + dja, r);
+            if (t == da) a_col = va;
+            dja += 1.0;
+            up = up_next;
+            r = r_next;
+        }
+        // both rows: step t computes a's column minj_a + t and b's column minj_a + t - 1 (same i + j)
+        for (; t < len_a; ++t) {
+            const double up_next = AT(shift + t + 1);
+            const double r_next = __ldg(rt + t + 1);
+            const double sum = dia + dja;
+            const double na = div_by_recip(NCB_DADD(NCB_DMUL(up, dia), NCB_DMUL(va, dja)), sum, r);
+            vb = div_by_recip(NCB_DADD(NCB_DMUL(a_col, dib), NCB_DMUL(vb, djb)), sum, r);
+            AT(t - da - 1) = vb;
+            va = na;
+            a_col = na;
+            dja += 1.0;
+            djb += 1.0;
+            up = up_next;
+            r = r_next;
+        }
+        // row b alone: its last one or two columns (the cell above the very last may lie right of a's band)
+        {
+            int u = max(len_a - da - 1, 0);
+            const double *rb = rtab + (i + 1) + minj_b;
+            if (len_a <= da) a_col = 1.0;
+            for (; u < len_b; ++u) {
+                vb = div_by_recip(NCB_DADD(NCB_DMUL(a_col, dib), NCB_DMUL(vb, djb)), dib + djb, __ldg(rb + u));
+                AT(u) = vb;
+                djb += 1.0;
+                a_col = 1.0;
+            }
+        }
+        curlen = len_b;
+        for (int jj = curlen; jj < len_p; ++jj) AT(jj) = 1.0;
+    }
+#endif
+    for (; result < 0.0 && i <= m; ++i) {
         const int lastminj = minj, lastlen = curlen;
         r_lo += ng;
         if (r_lo >= mg) { r_lo -= mg; ++q_lo; }
