@@ -131,8 +131,10 @@ __device__ __forceinline__ void derive12(const double (&r)[7], const double *tot
 // ---- initialisation ------------------------------------------------------------------------
 template <int SUB, int CAP>
 struct InitSmem {
-    float2 val[32 / SUB][CAP];
-    uint8_t k0[32 / SUB][CAP];     // 2-means assignment of a read: 1 = cluster 0
+    // + 8: the groups' rows start 64 bytes apart modulo the 128 bytes of the banks, so that the four
+    // 64-byte reads of a step fall on two wavefronts (the least possible), not four
+    float2 val[32 / SUB][CAP + 8];
+    uint8_t k0[32 / SUB][CAP + 8];     // 2-means assignment of a read: 1 = cluster 0
 };
 
 template <int SUB, int CAP, int WPC, int MINB>
@@ -306,7 +308,7 @@ gmm_init_kernel(NcbDeviceArgs a, WorkLists wl, int32_t *fetch, double *rec) {
 // ---- EM passes --------------------------------------------------------------------------------
 template <int SUB, int CAP>
 struct EmSmem {
-    float2 val[32 / SUB][CAP];
+    float2 val[32 / SUB][CAP + 8];     // + 8: see InitSmem
     double tot[32 / SUB][6];
 };
 
@@ -617,6 +619,9 @@ using namespace ncb;
 #ifndef NCB_GS_MINB_FINAL
 #define NCB_GS_MINB_FINAL 3
 #endif
+#ifndef NCB_GS_SUB_INIT
+#define NCB_GS_SUB_INIT 0     /* lanes per position of the initialisation kernel; 0: as the other two */
+#endif
 #ifndef NCB_GS_U_EM
 #define NCB_GS_U_EM 3         /* measured per 100 k positions of config 3: 1.244 ms (U = 1, 3 CTAs) / 1.209 (2, 2) / 1.207 (3, 2) */
 #endif
@@ -626,11 +631,13 @@ static int split_class(const NcbDeviceArgs &a, const WorkLists &wl, int32_t *f_i
                        int sm_count, cudaStream_t s, bool configure) {
     constexpr int WPC = NCB_GS_WPC, G = 32 / SUB;
     constexpr int MB_I = NCB_GS_MINB_INIT, MB_E = NCB_GS_MINB_EM, MB_F = NCB_GS_MINB_FINAL;
-    constexpr size_t sm_init = WPC * sizeof(InitSmem<SUB, CAP>), sm_em = WPC * sizeof(EmSmem<SUB, CAP>),
+    // the initialisation may use another number of lanes per position (the hand-over is per position)
+    constexpr int SUB_I = NCB_GS_SUB_INIT > 0 ? (NCB_GS_SUB_INIT > SUB ? NCB_GS_SUB_INIT : SUB) : SUB, G_I = 32 / SUB_I;
+    constexpr size_t sm_init = WPC * sizeof(InitSmem<SUB_I, CAP>), sm_em = WPC * sizeof(EmSmem<SUB, CAP>),
                      sm_final = WPC * G * sizeof(PosShared);
     static_assert(sm_init * MB_I + 1024 * MB_I <= 233472 && sm_em * MB_E + 1024 * MB_E <= 233472,
                   "split mixture kernels: the CTAs of an SM do not fit its shared memory");
-    auto k_init = gmm_init_kernel<SUB, CAP, WPC, MB_I>;
+    auto k_init = gmm_init_kernel<SUB_I, CAP, WPC, MB_I>;
     auto k_em = gmm_em_kernel<SUB, CAP, WPC, MB_E, F32, NCB_GS_U_EM>;
     auto k_final = gmm_final_kernel<SUB, WPC, MB_F, F32>;
     if (configure) {
@@ -640,14 +647,14 @@ static int split_class(const NcbDeviceArgs &a, const WorkLists &wl, int32_t *f_i
         return 0;
     }
     const int64_t P = a.n_positions;
-    const int64_t need = (P + WPC * G - 1) / (WPC * G);
-    auto grid = [&](int minb) {
+    auto grid = [&](int minb, int groups) {
+        const int64_t need = (P + WPC * groups - 1) / (WPC * groups);
         const int64_t cap = (int64_t)sm_count * minb;
         return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
     };
-    k_init<<<grid(MB_I), WPC * 32, sm_init, s>>>(a, wl, f_init, a.gmm_rec);
-    k_em<<<grid(MB_E), WPC * 32, sm_em, s>>>(a, wl, f_em, a.gmm_rec);
-    k_final<<<grid(MB_F), WPC * 32, sm_final, s>>>(a, wl, f_final, a.gmm_rec);
+    k_init<<<grid(MB_I, G_I), WPC * 32, sm_init, s>>>(a, wl, f_init, a.gmm_rec);
+    k_em<<<grid(MB_E, G), WPC * 32, sm_em, s>>>(a, wl, f_em, a.gmm_rec);
+    k_final<<<grid(MB_F, G), WPC * 32, sm_final, s>>>(a, wl, f_final, a.gmm_rec);
     return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
 
