@@ -1,9 +1,22 @@
 """
-Drop-in mirror of the reference's ``nanocompore/comparisons.py`` for the per-position
-two-condition comparison, running on the B200 kernels of libncb.
+Mirror of the reference's ``nanocompore/comparisons.py`` for the per-position two-condition
+comparison, running on the B200 kernels of libncb.
 
 Same names, signatures, config getters, result columns and error behaviour as the reference
-(/root/reference/nanocompore/comparisons.py):
+(/root/reference/nanocompore/comparisons.py).  What "same results" covers and what it does not:
+the shift statistics, the outlier filter, KS / MW / TT, the contingency arithmetic (LOR,
+chi-squared, counts from a given partition) and the BH correction are pinned on outputs of the
+unmodified reference; the MIXTURE FIT itself (``GMM_chi2_pvalue``, ``GMM_LOR``, the BIC gate and
+the ``*_mod`` / ``*_unmod`` counts) is NOT verified against the reference's fitter: gmm-gpu 0.2.8
+is neither vendored with the reference nor installable here.  The kernels implement this
+repository's own definition (oracle/gmm.py: scikit-learn's full-covariance EM, stop rule and BIC,
+started from a deterministic farthest-pair 2-means -- ``random_seed`` is accepted and ignored),
+so positions whose fit depends on the initialisation can get another p-value or another side of
+the BIC gate than upstream.  tests/test_gmm_gpu_parity.py makes the comparison wherever
+``gmm_gpu`` is importable; until it has run, the mixture columns are "definition-pinned", not
+drop-in.
+
+  Interface mirrored:
 
   * ``TranscriptComparator(config, worker, random_seed=42, dtype=torch.float32)``   :29-38
   * ``TranscriptComparator.compare_transcript(transcript, data, samples, conditions,
