@@ -27,8 +27,10 @@ Printed JSON (one line, rank 0):
             gather of keys + q-values on rank 0 sorted by key (sharding.gather_columns).  Wall clock,
             max over ranks, the job timed three times and the MEDIAN pass reported.  The transcripts of
             the job form ONE global list, sharded over the ranks by sharding.lpt_partition.
-  roofline  HBM roofline of the dominant kernel (mixture kernel), live CUDA-event timing; the fp64 / fp32
-            entries are the compute rooflines of the same kernel
+  roofline  HBM roofline of the kernel group of a batch that takes longest (live CUDA-event timing of the
+            statistics kernels and of each of the three mixture kernels; `kernels` lists all of them,
+            `mixture_fit` the three mixture kernels as one), `traffic` from the committed ncu capture; the
+            fp64 entries are the compute rooflines of the mixture kernels
   cpu_baseline  the reference's own code (baseline/_ref: comparisons.TranscriptComparator + the Worker
             prep functions, gmm_gpu restated by oracle/gmm.py) on one host core, bounded sample
   other_configs (N = 1)  BASELINE configs 2, 4 and 5 on the same GPU: value, e2e, roofline terms and a
@@ -623,62 +625,78 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the mixture kernel), HBM bound -------------------
-    # algorithmic bytes per launch of the mixture kernel: standardised values (8 B) + label
-    # (1 B) of every read once, offsets + read count (12 B) and the columns it writes
-    # (chi2 p, LOR, 2 x 4 cluster counts = 44 B) per position.  The statistics kernel moves
-    # 5 B/read in (int16 entries + label) and 8 B/read out plus 8 + 132 B per position.
+    # ---- roofline: every kernel group of a batch, the largest by live time on top ----------------
+    # Algorithmic bytes per launch: the statistics kernels read the int16 entries +
+    # label (5 B/read) and hand the standardised values to the mixture fit (8 B/read), 8 + 132 B per
+    # position of offsets and result columns; each of the three split mixture kernels reads the
+    # standardised values once (8 B/read; the final pass also the label) plus offsets / fit size (12 B)
+    # and the 21-double hand-over record of a position (written by init, read + 13 doubles rewritten by
+    # EM, read by the final pass, which writes 44 B of result columns).
     nb = max(totals['batches'], 1)
-    gmm_bytes = entries * 9 + P * (12 + 44)
-    stats_bytes = entries * (5 + 8) + P * (8 + 132)
-    ms_gmm, ms_stats = totals['ms_gmm'] / nb, totals['ms_stats'] / nb
     peak, peak_src = measured_peaks()
-    achieved = gmm_bytes / (ms_gmm / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "mixture kernels of a batch: ncb::position_kernel_warp<256, 8, 3, 1> (79 % of their time) + <128, 8, 2, 1>",
-                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
-                "algorithmic_bytes_per_launch": gmm_bytes, "ms_per_launch": ms_gmm,
-                "statistics_kernel": {"kernel": "statistics kernels of a batch: ncb::position_kernel_warp<256, 8, 3, 0> + <128, 8, 2, 0>",
-                                      "algorithmic_bytes_per_launch": stats_bytes, "ms_per_launch": ms_stats,
-                                      "achieved": stats_bytes / (ms_stats / 1000.0) / 1e9,
-                                      "frac": stats_bytes / (ms_stats / 1000.0) / 1e9 / peak},
-                "ms_ks_pvalue_kernels": totals['ms_ks'] / nb,
-                "ms_classify": totals['ms_classify'] / nb,
-                "note": "both kernels are issue / fp64-pipe bound (fp64 EM, sort), not HBM bound: "
-                        "DRAM traffic equals the algorithmic bytes and is ~1 % of peak; the fp64 entry "
-                        "is the compute roofline of the mixture kernel; see DESIGN.md"}
-    # compute roofline of the same kernel: fp64 operations per position counted by ncu
-    # (profiles/fp64_ops.json, thread-level DFMA/DADD/DMUL of the --set full capture) x the
-    # positions of a launch / the live launch time, against the fp64 rate measured by
-    # ncb_probe_fp64_peak in this run
-    ops_path = os.path.join(ROOT, 'profiles', 'fp64_ops.json')
-    fp64 = {"peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured (DFMA microbenchmark, this run)",
-            "achieved": None, "frac": None}
-    if os.path.exists(ops_path):
-        try:
-            with open(ops_path) as f:
-                ops = json.load(f)
-            flop = (2.0 * ops["dfma_per_position"] + ops["dadd_per_position"] + ops["dmul_per_position"]) * P
-            slots = (ops["dfma_per_position"] + ops["dadd_per_position"] + ops["dmul_per_position"]) * P
-            fp64["achieved"] = flop / (ms_gmm / 1000.0) / 1e12
-            fp64["frac"] = fp64["achieved"] / fp64_peak
-            # share of the fp64 pipe's issue slots (an add or a multiply takes the slot of an FMA)
-            fp64["pipe_frac"] = 2.0 * slots / (ms_gmm / 1000.0) / 1e12 / fp64_peak
-            fp64["flop_per_position"] = flop / P
-            fp64["ops_source"] = ops.get("source")
-        except Exception:
-            pass
-    roofline["fp64"] = fp64
-    ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(ncu_traffic):
-        try:
-            with open(ncu_traffic) as f:
-                tr = json.load(f)
-            # ncu capture at tr['positions'] positions per launch: scale per position
-            roofline["traffic"] = tr["dram_bytes_per_position"] * P
-            roofline["traffic_source"] = tr.get("source")
-        except Exception:
-            pass
+    traffic_src, ncu_traffic, ncu_pos = None, {}, 1
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            tr = json.load(f)
+        ncu_traffic, ncu_pos, traffic_src = tr["per_kernel"], tr["positions"], tr.get("source")
+    except Exception:
+        pass
+    fp64_ops, ops_src = {}, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'fp64_ops.json')) as f:
+            ops = json.load(f)
+        ops_src = ops.get("source")
+        for name, k in ops["kernels"].items():
+            fp64_ops[name.split('(')[0].replace('void ', '')] = k["fp64_thread_ops_per_position"]
+    except Exception:
+        pass
+
+    def group(kernels, algorithmic_bytes, ms):
+        """One roofline record: HBM terms from the live time; traffic (ncu, scaled to this batch) and
+        the fp64 terms when the committed ncu capture has these kernels."""
+        ach = algorithmic_bytes / (ms / 1000.0) / 1e9 if ms > 0 else None
+        rec = {"bound": "hbm", "kernel": ' + '.join(f"ncb::{k}" for k in kernels), "achieved": ach, "peak": peak,
+               "peak_source": peak_src, "unit": "GB/s", "frac": None if ach is None else ach / peak,
+               "traffic": None, "algorithmic_bytes_per_launch": algorithmic_bytes, "ms_per_launch": ms}
+        if all(k in ncu_traffic for k in kernels):
+            rec["traffic"] = sum(ncu_traffic[k] for k in kernels) * P / ncu_pos
+        if kernels and all(k in fp64_ops for k in kernels) and ms > 0:
+            dfma = sum(fp64_ops[k]["dfma"] for k in kernels)
+            other = sum(fp64_ops[k]["dadd"] + fp64_ops[k]["dmul"] for k in kernels)
+            flop = (2.0 * dfma + other) * P
+            rec["fp64"] = {"achieved": flop / (ms / 1000.0) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                           "frac": flop / (ms / 1000.0) / 1e12 / fp64_peak,
+                           # share of the fp64 pipe's issue slots (an add or a multiply takes the slot of an FMA)
+                           "pipe_frac": 2.0 * (dfma + other) * P / (ms / 1000.0) / 1e12 / fp64_peak,
+                           "flop_per_position": flop / P}
+        return rec
+
+    K_STATS = ["position_kernel_warp<256, 8, 3, 5>", "position_kernel_warp<128, 8, 2, 5>"]
+    K_INIT, K_EM, K_FINAL = "gmm_init_kernel<8, 256, 8, 3>", "gmm_em_kernel<8, 256, 8, 2, 0, 3>", "gmm_final_kernel<8, 8, 3, 0>"
+    ms_stats, ms_gmm = totals['ms_stats'] / nb, totals['ms_gmm'] / nb
+    groups = {
+        "statistics": group(K_STATS, entries * (5 + 8) + P * (8 + 132), ms_stats),
+        "mixture_init": group([K_INIT], entries * 8 + P * (12 + 21 * 8), totals['ms_gmm_init'] / nb),
+        "mixture_em": group([K_EM], entries * 8 + P * (12 + 21 * 8 + 13 * 8), totals['ms_gmm_em'] / nb),
+        "mixture_final": group([K_FINAL], entries * 9 + P * (12 + 21 * 8 + 44), totals['ms_gmm_final'] / nb),
+    }
+    top = max(groups, key=lambda g: groups[g]["ms_per_launch"])
+    roofline = dict(groups[top])
+    roofline["group"] = top
+    roofline["traffic_source"] = traffic_src
+    roofline["kernels"] = groups
+    # the mixture fit as a whole (what one fused kernel would have to move: every standardised value and
+    # label once, 56 B per position), against the time of its three kernels
+    roofline["mixture_fit"] = group([K_INIT, K_EM, K_FINAL], entries * 9 + P * (12 + 44), ms_gmm)
+    roofline["ms_ks_pvalue_kernels"] = totals['ms_ks'] / nb
+    roofline["ms_classify"] = totals['ms_classify'] / nb
+    roofline["fp64_peak"] = {"value": fp64_peak, "unit": "TFLOP/s", "source": "measured (DFMA microbenchmark, this run)",
+                             "ops_source": ops_src}
+    roofline["note"] = ("no kernel of the path is HBM bound (DRAM at 1-4 % of peak): the statistics kernels are bound by "
+                        "integer issue (sort, scans), the mixture kernels by the fp64 pipe -- their fp64 entries are the "
+                        "compute rooflines; the three mixture kernels each re-read the standardised values (traffic 3x the "
+                        "algorithmic bytes of a fused fit) in exchange for an instruction working set that fits the "
+                        "instruction cache; see DESIGN.md section 4")
 
     cpu = cpu_baseline_single_core(args.cpu_budget) if not args.no_cpu_baseline else None
 
@@ -700,7 +718,7 @@ def run_gpu_arm(args):
                 "stages_ms": stages, "includes": "H2D, kernels, D2H per batch; BH correction over all ranks' rows; "
                                                  "q-values to the host; gather of keys + q-values on rank 0"},
         "e2e_f32_wire": e2e_f32,
-        "em_fp32": dict(em_fp32, speedup_of_mixture_kernel=ms_gmm / em_fp32["ms_mixture_per_batch"]),
+        "em_fp32": dict(em_fp32, speedup_of_mixture_kernels=ms_gmm / em_fp32["ms_mixture_per_batch"]),
         "parity_spot_check": check,
         "gpu_launches": total_launches,
         "lpt": lpt,

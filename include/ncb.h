@@ -380,6 +380,10 @@ int ncb_last_timing(ncb_handle *h, float *ms_position_kernels, float *ms_ks_kern
  * those batches are done. */
 int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, double *ms_stats,
                       double *ms_gmm, double *ms_ks);
+/* The mixture share of ncb_timing_totals by kernel, over the same batches: initialisation (K = 1 fit,
+ * 2-means), EM passes, final pass + tests of the split mixture kernels of the warp size classes
+ * (csrc/gmm_split.cu); the kernels of larger classes count with the final pass. */
+int ncb_timing_mixture(ncb_handle *h, double *ms_init, double *ms_em, double *ms_final);
 
 /* Non-tensor fp64 rate of the device in TFLOP/s, measured with a register-resident DFMA
  * microbenchmark (best of 3 after a warm-up): the compute roofline the fp64 mixture kernel is

@@ -50,7 +50,7 @@ EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_results_host_bytes',
            'ncb_pack_fill_i16', 'ncb_pack_rows_fill_i16', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr', 'ncb_bh_fdr_segment',
            'ncb_context_combine',
-           'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals',
+           'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals', 'ncb_timing_mixture',
            'ncb_pack_count', 'ncb_pack_fill', 'ncb_pack_rows_count', 'ncb_pack_rows_fill',
            'ncb_rows_invalid_ratio', 'ncb_bam_open', 'ncb_bam_close', 'ncb_bam_last_error',
            'ncb_bam_n_references', 'ncb_bam_reference_name', 'ncb_bam_reference_length',
@@ -131,6 +131,8 @@ def load(path=None):
     lib.ncb_last_timing.restype = C.c_int
     lib.ncb_timing_totals.argtypes = [vp, C.POINTER(i64)] + [C.POINTER(C.c_double)] * 4
     lib.ncb_timing_totals.restype = C.c_int
+    lib.ncb_timing_mixture.argtypes = [vp] + [C.POINTER(C.c_double)] * 3
+    lib.ncb_timing_mixture.restype = C.c_int
     lib.ncb_pack_count.argtypes = [vp, i64, i32, i32, vp, C.c_int]
     lib.ncb_pack_count.restype = C.c_int
     lib.ncb_pack_fill.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, C.c_int]

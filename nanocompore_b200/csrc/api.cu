@@ -24,9 +24,9 @@ struct ncb_handle {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // events of the last timed batch
+    cudaEvent_t ev[NCB_TIMING_EVENTS] = {};   // events of the last timed batch
     bool timed = false;
-    std::vector<cudaEvent_t> ev_log;   // 5 events per timed batch since ncb_set_timing(h, 1)
+    std::vector<cudaEvent_t> ev_log;   // NCB_TIMING_EVENTS events per timed batch since ncb_set_timing(h, 1)
     // the exact-KS kernels of a batch depend on its statistics kernels only: they run on this
     // stream next to the mixture kernels (fork after the statistics phase, join before the results)
     cudaStream_t aux = nullptr;
@@ -310,9 +310,9 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
 
     // the timing log holds at most NCB_TIMING_LOG_MAX batches: later batches run untimed (a process
     // that leaves NCB_TIMING=1 on for a whole run does not accumulate events without bound)
-    const bool time_it = h->timing != 0 && h->ev_log.size() < 5 * (size_t)NCB_TIMING_LOG_MAX;
+    const bool time_it = h->timing != 0 && h->ev_log.size() < NCB_TIMING_EVENTS * (size_t)NCB_TIMING_LOG_MAX;
     if (time_it) {
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < NCB_TIMING_EVENTS; ++i) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             try {   // nothing is thrown across the C ABI
@@ -430,7 +430,8 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     // kernels on the caller's, joined before the results are copied out.  Timed batches keep
     // everything on one stream so that the events bracket each group of kernels alone.
     const bool fork = !time_it && any_ks && a.zbuf;
-    n = ncb_launch_position_kernels(a, wl, h->sm_count, s, time_it ? h->ev[2] : nullptr, fork ? 1 : 3);
+    n = ncb_launch_position_kernels(a, wl, h->sm_count, s, time_it ? h->ev[2] : nullptr, fork ? 1 : 3,
+                                    time_it ? &h->ev[5] : nullptr);
     if (n < 0) return fail(h, NCB_ERR_CUDA, "position kernel launch", cudaGetLastError());
     h->launches += n;
     if (time_it) CK(cudaEventRecord(h->ev[3], s));
@@ -689,9 +690,9 @@ int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, do
     if (!h) return NCB_ERR_INVALID;
     ON_DEVICE(h);
     double a = 0, b = 0, c = 0, d = 0;
-    const size_t nb = h->ev_log.size() / 5;
+    const size_t nb = h->ev_log.size() / NCB_TIMING_EVENTS;
     for (size_t i = 0; i < nb; ++i) {
-        cudaEvent_t *e = &h->ev_log[5 * i];
+        cudaEvent_t *e = &h->ev_log[NCB_TIMING_EVENTS * i];
         CK(cudaEventSynchronize(e[4]));
         float x = 0, y = 0, z = 0, w = 0;
         CK(cudaEventElapsedTime(&x, e[0], e[1]));
@@ -705,6 +706,28 @@ int ncb_timing_totals(ncb_handle *h, int64_t *n_batches, double *ms_classify, do
     if (ms_stats) *ms_stats = b;
     if (ms_gmm) *ms_gmm = c;
     if (ms_ks) *ms_ks = d;
+    return NCB_OK;
+}
+
+int ncb_timing_mixture(ncb_handle *h, double *ms_init, double *ms_em, double *ms_final) {
+    if (!h) return NCB_ERR_INVALID;
+    ON_DEVICE(h);
+    double a = 0, b = 0, c = 0;
+    const size_t nb = h->ev_log.size() / NCB_TIMING_EVENTS;
+    for (size_t i = 0; i < nb; ++i) {
+        cudaEvent_t *e = &h->ev_log[NCB_TIMING_EVENTS * i];
+        CK(cudaEventSynchronize(e[4]));
+        float x = 0, y = 0, z = 0;
+        // e[5] / e[6]: after the initialisation / the EM kernel of the narrow warp classes; batches whose
+        // mixture fit did not go through the split kernels recorded both together with e[2]
+        CK(cudaEventElapsedTime(&x, e[2], e[5]));
+        CK(cudaEventElapsedTime(&y, e[5], e[6]));
+        CK(cudaEventElapsedTime(&z, e[6], e[3]));
+        a += x; b += y; c += z;
+    }
+    if (ms_init) *ms_init = a;
+    if (ms_em) *ms_em = b;
+    if (ms_final) *ms_final = c;
     return NCB_OK;
 }
 

@@ -628,7 +628,7 @@ using namespace ncb;
 
 template <int SUB, int CAP, bool F32>
 static int split_class(const NcbDeviceArgs &a, const WorkLists &wl, int32_t *f_init, int32_t *f_em, int32_t *f_final,
-                       int sm_count, cudaStream_t s, bool configure) {
+                       int sm_count, cudaStream_t s, bool configure, cudaEvent_t *marks) {
     constexpr int WPC = NCB_GS_WPC, G = 32 / SUB;
     constexpr int MB_I = NCB_GS_MINB_INIT, MB_E = NCB_GS_MINB_EM, MB_F = NCB_GS_MINB_FINAL;
     // the initialisation may use another number of lanes per position (the hand-over is per position)
@@ -653,7 +653,9 @@ static int split_class(const NcbDeviceArgs &a, const WorkLists &wl, int32_t *f_i
         return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
     };
     k_init<<<grid(MB_I, G_I), WPC * 32, sm_init, s>>>(a, wl, f_init, a.gmm_rec);
+    if (marks) cudaEventRecord(marks[0], s);
     k_em<<<grid(MB_E, G), WPC * 32, sm_em, s>>>(a, wl, f_em, a.gmm_rec);
+    if (marks) cudaEventRecord(marks[1], s);
     k_final<<<grid(MB_F, G), WPC * 32, sm_final, s>>>(a, wl, f_final, a.gmm_rec);
     return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
@@ -661,7 +663,8 @@ static int split_class(const NcbDeviceArgs &a, const WorkLists &wl, int32_t *f_i
 // `wide`: the class of up to 512 reads (16 lanes per position); else the classes of up to 128 and up to
 // 256 reads as one launch (8 lanes per position).  The work counters are those of the larger class.
 template <bool F32>
-static int split_all(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s, bool configure) {
+static int split_all(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s, bool configure,
+                     cudaEvent_t *marks = nullptr) {
     const int64_t P = a.n_positions;
     const int cls = wide ? 2 : 1;
     WorkLists wl{};
@@ -677,8 +680,8 @@ static int split_all(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, i
         f_em = w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM_EM) + cls;
         f_final = w.class_count + NCB_NUM_CLASSES * (1 + NCB_PHASE_GMM_FINAL) + cls;
     }
-    return wide ? split_class<NCB_GS_SUB2, 512, F32>(a, wl, f_init, f_em, f_final, sm_count, s, configure)
-                : split_class<NCB_GS_SUB1, 256, F32>(a, wl, f_init, f_em, f_final, sm_count, s, configure);
+    return wide ? split_class<NCB_GS_SUB2, 512, F32>(a, wl, f_init, f_em, f_final, sm_count, s, configure, marks)
+                : split_class<NCB_GS_SUB1, 256, F32>(a, wl, f_init, f_em, f_final, sm_count, s, configure, marks);
 }
 
 int ncb_configure_gmm_split(void) {
@@ -689,6 +692,8 @@ int ncb_configure_gmm_split(void) {
     return 0;
 }
 
-int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s) {
-    return a.em_fp32 ? split_all<true>(a, w, wide, sm_count, s, false) : split_all<false>(a, w, wide, sm_count, s, false);
+int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s,
+                         cudaEvent_t *marks) {
+    return a.em_fp32 ? split_all<true>(a, w, wide, sm_count, s, false, marks)
+                     : split_all<false>(a, w, wide, sm_count, s, false, marks);
 }

@@ -65,6 +65,7 @@ struct NcbDeviceArgs {
 // after the other on its stream, so they share the rows); a group whose row would not fit keeps the flag
 #define NCB_MW_SCRATCH_PER_SM (4 * (int64_t)NCB_MAX_READS + 8)
 #define NCB_TIMING_LOG_MAX 4096   /* batches kept in a handle's timing log */
+#define NCB_TIMING_EVENTS 7       /* start, classify, statistics, mixture, exact KS; mixture: after init, after EM */
 // phases (each has its own work counter per class): statistics / mixture, 2 / 3 variables; the mixture
 // phase of the warp classes is three kernels (gmm_split.cu): initialisation (the counter of
 // NCB_PHASE_GMM), EM passes, final pass
@@ -112,9 +113,10 @@ struct NcbKsWork {
 // launchers (each returns the number of kernels launched, or <0 on launch error)
 int ncb_launch_classify(const NcbDeviceArgs &a, const NcbWorklists &w, cudaStream_t s);
 // phases & 1: statistics kernels; phases & 2: (if a.zbuf) mixture kernels; `between` (optional) is
-// recorded after the statistics kernels
+// recorded after the statistics kernels; `marks` (optional): two events recorded after the initialisation
+// and after the EM kernel of the split mixture fit (with `between` when that fit does not run)
 int ncb_launch_position_kernels(const NcbDeviceArgs &a, const NcbWorklists &w, int sm_count,
-                                cudaStream_t s, cudaEvent_t between, int phases);
+                                cudaStream_t s, cudaEvent_t between, int phases, cudaEvent_t *marks = nullptr);
 int ncb_launch_ks_pvalues(int64_t n_problems, const int32_t *n0, const int32_t *n1,
                           const int64_t *h, double *p_out, const NcbKsWork &w, int sm_count,
                           cudaStream_t s);
@@ -133,4 +135,6 @@ int ncb_configure_kernels(void);  // cudaFuncSetAttribute for large dynamic shar
 // mixture fit of the warp size classes as three kernels (gmm_split.cu): classes 0 and 1 in one launch of
 // each, class 2 (`wide`) in its own; returns the number launched
 int ncb_configure_gmm_split(void);
-int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s);
+// marks (or NULL): two events, recorded after the initialisation and after the EM kernel
+int ncb_launch_gmm_split(const NcbDeviceArgs &a, const NcbWorklists &w, bool wide, int sm_count, cudaStream_t s,
+                         cudaEvent_t *marks);

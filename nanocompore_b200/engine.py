@@ -493,5 +493,8 @@ class Engine:
         n, a, b, c, d = C.c_int64(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
         self._check(self.lib.ncb_timing_totals(self._handle, C.byref(n), C.byref(a), C.byref(b),
                                                C.byref(c), C.byref(d)))
+        i, e, f = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.ncb_timing_mixture(self._handle, C.byref(i), C.byref(e), C.byref(f)))
         return dict(batches=n.value, ms_classify=a.value, ms_stats=b.value, ms_gmm=c.value,
-                    ms_position=b.value + c.value, ms_ks=d.value)
+                    ms_position=b.value + c.value, ms_ks=d.value,
+                    ms_gmm_init=i.value, ms_gmm_em=e.value, ms_gmm_final=f.value)
