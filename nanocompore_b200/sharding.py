@@ -81,6 +81,14 @@ def _all_counts(n_local, device, group, world):
 FDR_SAMPLE = 4096      # numbers every rank contributes to the splitter sample of a column
 
 
+def sample_rows(n, k, device=None):
+    """``k`` evenly spaced row indices of 0 .. n - 1 (first and last included), in integer arithmetic:
+    a float32 ``linspace`` cannot represent the last row of a shard of more than 2^24 rows and rounds it
+    past the end (64 M rows per rank in bench.py's job)."""
+    i = torch.arange(k, dtype=torch.int64, device=device)
+    return (i * (n - 1)) // max(k - 1, 1)
+
+
 def fdr_columns(cols, bh, group=None):
     """Benjamini-Hochberg q-values of p-value columns whose rows are spread over the ranks.
 
@@ -112,8 +120,7 @@ def fdr_columns(cols, bh, group=None):
         v = col[rows]
         # splitters: FDR_SAMPLE numbers of every rank (evenly spaced rows; NaN where a rank has none)
         if v.numel():
-            pick = torch.linspace(0, v.numel() - 1, FDR_SAMPLE, device=device).round().long()
-            mine = v[pick]
+            mine = v[sample_rows(v.numel(), FDR_SAMPLE, device)]
         else:
             mine = torch.full((FDR_SAMPLE,), float('nan'), dtype=cols.dtype, device=device)
         pooled = torch.empty(world * FDR_SAMPLE, dtype=cols.dtype, device=device)

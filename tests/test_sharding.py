@@ -8,6 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from nanocompore_b200 import sharding
 from nanocompore_b200.sharding import (fdr_columns, gather_columns, lpt_imbalance, lpt_partition, warm_up,
                                        work_estimate)
 
@@ -162,3 +163,13 @@ def test_lpt_imbalance():
     shards = lpt_partition(w, 2)
     assert lpt_imbalance(w, shards) == 1.0
     assert lpt_imbalance(w, [np.array([0, 1]), np.array([2, 3])]) == pytest.approx(1.4)
+
+
+def test_sample_rows_stays_inside_large_shards():
+    """The splitter sample of fdr_columns on shards beyond 2^24 rows (bench.py: 64 M rows per rank): a
+    float32 linspace rounds the last index past the end there."""
+    for n in (1, 2, 4095, 4096, 4097, (1 << 24) + 1, 63_999_999, 64_000_000, (1 << 31) + 5):
+        pick = sharding.sample_rows(n, sharding.FDR_SAMPLE)
+        assert pick.dtype == torch.int64 and pick.numel() == sharding.FDR_SAMPLE
+        assert int(pick[0]) == 0 and int(pick[-1]) == n - 1
+        assert bool((pick[1:] >= pick[:-1]).all()) and int(pick.max()) < n
