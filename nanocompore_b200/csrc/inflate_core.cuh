@@ -44,7 +44,8 @@ struct Tables {
     uint8_t lens[MAX_LIT + MAX_DIST];   // code lengths of the block: literal/length codes, then distance codes
     uint16_t code[MAX_LIT + MAX_DIST];  // their canonical codes, most significant bit first
     uint16_t cmd_len[MAX_CMDS];         // command queue: bytes the command produces (1 = literal)
-    uint16_t cmd_val[MAX_CMDS];         // literal byte, or the distance of a copy
+    uint16_t cmd_val[MAX_CMDS];         // literal byte, or the distance of a copy - 1
+    uint16_t cmd_off[MAX_CMDS + 1];     // first output byte of the command, relative to the batch; [n] = bytes of the batch
     int32_t n_lit, n_dist;              // codes of the current block
 };
 
@@ -77,6 +78,14 @@ struct BitReader {
         return v;
     }
     NCB_HD int64_t consumed() const { return (int64_t)next * 32 - cnt; }
+    NCB_HD void align_to_byte() { drop(cnt & 7); }
+    NCB_HD void seek_byte(int64_t byte) {      // continue at a byte position of the payload
+        next = (uint32_t)(byte >> 2);
+        buf = 0;
+        cnt = 0;
+        const int rest = (int)(byte & 3) * 8;
+        if (rest) { need(rest); drop(rest); }
+    }
     NCB_HD bool overrun() const { return consumed() > limit_bits; }
 };
 
@@ -257,8 +266,10 @@ NCB_HD int decode_commands(BitReader &br, Tables &t, int64_t produced, int64_t u
     const uint8_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12,
                                     12, 13, 13};
     int n = 0;
+    const int64_t start = produced;
     *end_of_block = false;
     *err = INF_OK;
+    t.cmd_off[0] = 0;
     while (n < MAX_CMDS) {
         const int sym = decode_lit(br, t);
         if (sym < 0) { *err = INF_ERR_CODE; break; }
@@ -267,7 +278,7 @@ NCB_HD int decode_commands(BitReader &br, Tables &t, int64_t produced, int64_t u
             t.cmd_len[n] = 1;
             t.cmd_val[n] = (uint16_t)sym;
             produced += 1;
-            ++n;
+            t.cmd_off[++n] = (uint16_t)(produced - start);
         } else if (sym == 256) {
             *end_of_block = true;
             break;
@@ -281,14 +292,129 @@ NCB_HD int decode_commands(BitReader &br, Tables &t, int64_t produced, int64_t u
             if ((int64_t)dist > produced) { *err = INF_ERR_DIST; break; }
             if (produced + len > usize) { *err = INF_ERR_OUTPUT; break; }
             t.cmd_len[n] = (uint16_t)len;
-            t.cmd_val[n] = (uint16_t)dist;      // a distance is at most 32768: stored as dist - 1
-            t.cmd_val[n] = (uint16_t)(dist - 1);
+            t.cmd_val[n] = (uint16_t)(dist - 1);      // a distance is at most 32768
             produced += len;
-            ++n;
+            t.cmd_off[++n] = (uint16_t)(produced - start);
         }
         if (br.overrun()) { *err = INF_ERR_INPUT; break; }
     }
+    // the end-of-block code, too, has to lie inside the payload (zeros are read behind it, and seven
+    // zero bits are the end-of-block code of the fixed code)
+    if (*err == INF_OK && br.overrun()) *err = INF_ERR_INPUT;
     return n;
 }
+
+
+// ---- one member, by a "warp" W ------------------------------------------------------------------
+// W provides lane() / stride() (the lanes share strided loops), leader() (the lane that walks the bit
+// stream), bcast(int) (the leader's value on every lane), sync() (orders the lanes' accesses to the
+// tables and to the output) and load_out(p) (a byte of the output written earlier by any lane).  On
+// the device W is a CUDA warp (decode.cu); on the host one lane with stride 1 (the test harness).
+// 32 commands of 258 bytes fit the 16-bit offsets of the queue.
+template <class W>
+NCB_HD int inflate_member(W &w, Tables &t, const uint32_t *words, uint32_t n_words, int64_t cbytes,
+                          uint8_t *out, int64_t usize) {
+    BitReader br;
+    br.init(words, n_words, cbytes);
+    const uint8_t *in_bytes = reinterpret_cast<const uint8_t *>(words);
+    int64_t produced = 0;
+    int err = INF_OK, final_block = 0;
+    while (!final_block && !err) {
+        int btype = 0;
+        if (w.leader()) {
+            final_block = (int)br.take(1);
+            btype = (int)br.take(2);
+            if (br.overrun()) err = INF_ERR_INPUT;
+        }
+        final_block = w.bcast(final_block);
+        btype = w.bcast(btype);
+        err = w.bcast(err);
+        if (err) break;
+        if (btype == 0) {
+            int len = 0, from = 0;
+            if (w.leader()) {
+                br.align_to_byte();
+                len = (int)br.take(16);
+                const int nlen = (int)br.take(16);
+                from = (int)(br.consumed() >> 3);
+                if ((len ^ nlen) != 0xffff) err = INF_ERR_STORED;
+                else if ((int64_t)from + len > cbytes) err = INF_ERR_INPUT;
+                else if (produced + len > usize) err = INF_ERR_OUTPUT;
+                else br.seek_byte((int64_t)from + len);
+            }
+            len = w.bcast(len);
+            from = w.bcast(from);
+            err = w.bcast(err);
+            if (err) break;
+            for (int i = w.lane(); i < len; i += w.stride()) out[produced + i] = in_bytes[from + i];
+            produced += len;
+            w.sync();
+            continue;
+        }
+        if (btype == 3) { err = INF_ERR_BTYPE; break; }
+        if (w.leader()) {
+            if (btype == 1) fixed_lengths(t);
+            else err = read_dynamic_header(br, t);
+            if (!err) err = build_block_codes(t);
+        }
+        err = w.bcast(err);
+        if (err) break;
+        for (int i = w.lane(); i < (1 << LIT_BITS); i += w.stride()) t.lit_lut[i] = 0;
+        for (int i = w.lane(); i < (1 << DIST_BITS); i += w.stride()) t.dist_lut[i] = 0;
+        w.sync();
+        fill_lit_lut(t, w.lane(), w.stride());
+        fill_dist_lut(t, w.lane(), w.stride());
+        w.sync();
+        int eob = 0;
+        while (!eob && !err) {
+            int n = 0;
+            if (w.leader()) {
+                bool e = false;
+                n = decode_commands(br, t, produced, usize, &e, &err);
+                eob = e ? 1 : 0;
+            }
+            n = w.bcast(n);
+            eob = w.bcast(eob);
+            err = w.bcast(err);
+            if (err) break;
+            w.sync();
+            // literals first: every lane its own bytes
+            int copies = 0;
+            for (int j = w.lane(); j < n; j += w.stride()) {
+                if (t.cmd_len[j] == 1) out[produced + t.cmd_off[j]] = (uint8_t)t.cmd_val[j];
+                else copies = 1;
+            }
+            if (w.any(copies)) {
+                w.sync();
+                // copies in stream order: byte i of a copy is the byte dist behind it, i.e. byte i mod dist of
+                // the dist bytes before its start -- all written before this command
+                for (int j = 0; j < n; ++j) {
+                    const int len = t.cmd_len[j];
+                    if (len == 1) continue;
+                    const int dist = (int)t.cmd_val[j] + 1;
+                    uint8_t *dst = out + produced + t.cmd_off[j];
+                    const uint8_t *src = dst - dist;
+                    for (int i = w.lane(); i < len; i += w.stride()) dst[i] = w.load_out(src + (dist >= len ? i : i % dist));
+                    w.sync();
+                }
+            }
+            produced += t.cmd_off[n];
+            w.sync();
+        }
+    }
+    if (!err && produced != usize) err = INF_ERR_OUTPUT;
+    return err;
+}
+
+// the host's "warp": one lane
+struct SerialWarp {
+    NCB_HD int lane() const { return 0; }
+    NCB_HD int stride() const { return 1; }
+    NCB_HD bool leader() const { return true; }
+    NCB_HD int bcast(int v) const { return v; }
+    NCB_HD bool any(int v) const { return v != 0; }
+    NCB_HD void sync() const {}
+    NCB_HD uint8_t load_out(const uint8_t *p) const { return *p; }
+};
 
 }  // namespace ncb_inflate
