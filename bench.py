@@ -578,6 +578,25 @@ def run_gpu_arm(args):
                 {"compare_ms": (t1 - t0) * 1000.0, "fdr_ms": (t2 - t1) * 1000.0,
                  "gather_ms": (t3 - t2) * 1000.0}, info)
 
+    def critical_path(stages):
+        """The stage times of the rank that finishes its compare stage LAST, plus the spread of that stage
+        over the ranks.  (A rank that is through its batches early waits inside the first collective of
+        the correction for the slowest one: the maximum over ranks of every stage separately would add
+        that wait to the correction and the parts would not sum to the job.)"""
+        if world == 1:
+            return stages
+        names = sorted(stages)
+        mine = torch.tensor([stages[k] for k in names], dtype=torch.float64, device=dev)
+        table = torch.empty((world, len(names)), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(table.view(-1), mine)
+        table = table.cpu().numpy()
+        c = names.index('compare_ms')
+        slow = int(np.argmax(table[:, c]))
+        out = {k: float(table[slow, i]) for i, k in enumerate(names)}
+        out["critical_rank"] = slow
+        out["compare_ms_fastest_rank"] = float(table[:, c].min())
+        return out
+
     import gc
     gc.collect()
     gc.disable()            # a collection inside the wall-clock region would be charged to the path
@@ -586,7 +605,7 @@ def run_gpu_arm(args):
     passes = []
     for _ in range(E2E_REPEATS):
         ms, tested_host, stages, ginfo = job_pass(order_k, n_rows_job)
-        passes.append((max_over_ranks(ms), tested_host, {k: max_over_ranks(v) for k, v in stages.items()}, ginfo))
+        passes.append((max_over_ranks(ms), tested_host, critical_path(stages), ginfo))
     gc.enable()
     passes.sort(key=lambda x: x[0])
     ms_e2e, tested_host, stages, ginfo = passes[len(passes) // 2]
@@ -595,7 +614,36 @@ def run_gpu_arm(args):
     e2e_value = total_tested_host / (ms_e2e / 1000.0)
     total_launches = int(sum_over_ranks(float(launches)))
     fdr_h2d_batch = len(pv_rows) * 8 * P               # the p-value columns go back up for the correction
+    # where the correction spends its time: one more pass with a synchronisation after every stage
+    # (diagnostic, outside the timed passes)
+    fdr_stages = {}
+    if world > 1:
+        sharding.fdr_columns(job_p[:, :n_rows_job], bh, timings=fdr_stages)
+        fdr_stages = {k: max_over_ranks(v) for k, v in sorted(fdr_stages.items())}
     del job_p, keys
+
+    # what the host of this box gives N ranks at once: the signal arrays of the same pinned batches copied
+    # to the device with no kernel in between, all ranks together -- the ceiling of the end-to-end figure
+    # when the link, not the kernels, bounds it
+    def h2d_ceiling():
+        stage = [torch.empty_like(host_pool[0].signal, device=dev) for _ in range(2)]
+        n_rows = min(b.signal.shape[0] for b in host_pool)
+        copies = 4 * n_pool
+        def run():
+            for i in range(copies):
+                stage[i % 2][:n_rows].copy_(host_pool[i % n_pool].signal[:n_rows], non_blocking=True)
+        run()
+        barrier()
+        t0 = time.perf_counter()
+        run()
+        torch.cuda.synchronize(dev)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        nbytes = copies * n_rows * host_pool[0].signal.shape[1] * host_pool[0].signal.element_size()
+        per_rank = nbytes / dt / 1e9
+        return {"per_rank_GBps": per_rank, "aggregate_GBps": per_rank * world, "ranks": world,
+                "bytes_per_rank": nbytes}
+    h2d_probe = h2d_ceiling()
+    e2e_h2d_GBps = (h2d_batch + fdr_h2d_batch) * B * K / (stages["compare_ms"] / 1000.0) / 1e9
 
     # float32 wire (9 bytes per entry) on the same data, one pass of the compare stage: what the
     # int16 wire buys end to end
@@ -717,6 +765,8 @@ def run_gpu_arm(args):
                 "job_ms": ms_e2e, "passes_job_ms": [p[0] for p in passes], "reported": "median pass",
                 "stages_ms": stages, "includes": "H2D, kernels, D2H per batch; BH correction over all ranks' rows; "
                                                  "q-values to the host; gather of keys + q-values on rank 0"},
+        "h2d": {"probe_all_ranks_copying": h2d_probe, "per_rank_GBps_in_the_compare_stage_of_the_job": e2e_h2d_GBps,
+                "share_of_probe": e2e_h2d_GBps / h2d_probe["per_rank_GBps"]},
         "e2e_f32_wire": e2e_f32,
         "em_fp32": dict(em_fp32, speedup_of_mixture_kernels=ms_gmm / em_fp32["ms_mixture_per_batch"]),
         "parity_spot_check": check,
@@ -725,7 +775,8 @@ def run_gpu_arm(args):
         "final_gather": None if ginfo is None else dict(ginfo, ms=stages["gather_ms"],
                                                         share_of_job=stages["gather_ms"] / ms_e2e),
         "fdr": {"ms": stages["fdr_ms"], "share_of_job": stages["fdr_ms"] / ms_e2e,
-                "rows": int(n_rows_job * world), "columns": len(pv_rows)},
+                "rows": int(n_rows_job * world), "columns": len(pv_rows),
+                "stages_ms_diagnostic_pass": fdr_stages or None},
         "job_skew": job_skew,
         "other_configs": other,
         "clocks": clocks,

@@ -366,6 +366,49 @@ int64_t ncb_bam_read_uncalled4(ncb_bam *b, int32_t ref, int64_t ref_len, int32_t
                                int32_t kit_center, float *intensity, float *dwell, char *names,
                                int32_t name_stride, int64_t max_reads);
 
+/* --- device-side Uncalled4 decoder (csrc/decode.cu) -----------------------------------------
+ * The same step as ncb_bam_read_uncalled4 + ncb_pack_rows_* for a whole batch of transcripts, with the
+ * work on the GPU: the host looks the BGZF members of the transcripts up in the handles' indexes and
+ * copies their COMPRESSED bytes into pinned memory (ncb_decoder_stage, no GPU work, may run on another
+ * thread while the device works on the batch of another slot); ncb_decoder_launch enqueues the upload
+ * and the kernels -- inflate, record walk, tag decoding (uncalled4.py:118-201), invalid-kmer filter
+ * (common.py:298-329, run.py:711-718), read order (run.py:698-700), CSR assembly -- and fills `batch`
+ * with a DEVICE-resident NCB_LAYOUT_CSR_I16 batch that ncb_compare takes on the same stream (the
+ * pointers belong to the slot and stay valid until its next ncb_decoder_stage).  Positions of the batch:
+ * transcript after transcript, ref_len[t] positions each.
+ *
+ *   file_label  NCB_LABEL(condition, sample) of every file; files in the order of the config's `data`
+ *               section (equal read names keep that order, readers.Uncalled4Reader)
+ *   refs        [n_tx][n_files] reference index of the transcript in the file (ncb_bam_reference_index),
+ *               < 0: none
+ *
+ * ncb_decoder_collect waits for the slot's kernels and reports per transcript the reads kept and a flag:
+ * 0 = decoded; NCB_DECODE_ERROR = a member does not inflate or a record / tag is malformed;
+ * NCB_DECODE_NEEDS_HOST = well-formed input this path does not reproduce to the bit (values that are no
+ * int16 codes, overlapping or more than 48 ur segments, non-ASCII read names).  A flagged transcript has
+ * no entries in the batch: the caller reads it with ncb_bam_read_uncalled4, which also owns the error
+ * messages.  Downsampling (run.py:518-529) is not done here: transcripts with more records than
+ * `downsample_high_coverage` belong to the host path as well. */
+typedef struct ncb_decoder ncb_decoder;
+enum { NCB_DECODE_OK = 0, NCB_DECODE_ERROR = 1, NCB_DECODE_NEEDS_HOST = 2 };
+int ncb_decoder_create(ncb_decoder **out, int device, int n_slots);
+void ncb_decoder_destroy(ncb_decoder *d);
+const char *ncb_decoder_last_error(const ncb_decoder *d);
+int ncb_decoder_stage(ncb_decoder *d, int slot, int32_t n_files, ncb_bam *const *bams, const uint8_t *file_label,
+                      int32_t n_tx, const int32_t *refs, const int64_t *ref_len, int threads);
+int ncb_decoder_launch(ncb_decoder *d, int slot, int32_t kit_len, int32_t kit_center, int32_t motor_offset,
+                       double max_invalid_ratio, ncb_batch *batch, void *stream);
+int ncb_decoder_collect(ncb_decoder *d, int slot, int32_t *tx_flags, int32_t *tx_reads, int64_t *n_entries);
+/* Compressed bytes staged in the slot (what ncb_decoder_launch uploads); optionally the inflated bytes,
+ * BGZF members and records behind them.  -1: nothing staged. */
+int64_t ncb_decoder_staged_bytes(const ncb_decoder *d, int slot, int64_t *text_bytes, int64_t *n_members,
+                                 int64_t *n_records);
+int64_t ncb_decoder_kernel_launches(const ncb_decoder *d, int slot);
+/* The slot's batch copied to host arrays (tests, debugging): waits for the slot's kernels.  pos_offsets
+ * [P + 1]; signal int16 [E][n_vars] and label [E] with E = pos_offsets[P] <= cap_entries. */
+int ncb_decoder_download(ncb_decoder *d, int slot, int64_t *pos_offsets, int16_t *signal, uint8_t *label,
+                         int64_t cap_entries, int32_t n_vars);
+
 /* --- introspection ---------------------------------------------------------------- */
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */

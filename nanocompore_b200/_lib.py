@@ -27,6 +27,7 @@ NCB_POS_AUTO_GMM = 256
 NCB_POS_MW_EXACT_SKIPPED = 512
 NCB_CTX_MAX = 8
 NCB_CTX_OK, NCB_CTX_TOO_SHORT, NCB_CTX_INVALID_PVALUE = 0, 1, 2
+NCB_DECODE_OK, NCB_DECODE_ERROR, NCB_DECODE_NEEDS_HOST = 0, 1, 2
 
 PV = dict(KS_INTENSITY=0, KS_DWELL=1, MW_INTENSITY=2, MW_DWELL=3, TT_INTENSITY=4, TT_DWELL=5,
           GMM_CHI2=6, GMM_LOGIT=7, GMM_LOGIT_COEF=8)
@@ -55,7 +56,10 @@ EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 
            'ncb_rows_invalid_ratio', 'ncb_bam_open', 'ncb_bam_close', 'ncb_bam_last_error',
            'ncb_bam_n_references', 'ncb_bam_reference_name', 'ncb_bam_reference_length',
            'ncb_bam_reference_records', 'ncb_bam_reference_index', 'ncb_bam_read_uncalled4',
-           'ncb_probe_fp64_peak']
+           'ncb_probe_fp64_peak',
+           'ncb_decoder_create', 'ncb_decoder_destroy', 'ncb_decoder_last_error', 'ncb_decoder_stage',
+           'ncb_decoder_launch', 'ncb_decoder_collect', 'ncb_decoder_staged_bytes', 'ncb_decoder_kernel_launches',
+           'ncb_decoder_download']
 
 
 class NcbOpts(C.Structure):
@@ -169,6 +173,24 @@ def load(path=None):
     lib.ncb_bam_read_uncalled4.restype = i64
     lib.ncb_probe_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     lib.ncb_probe_fp64_peak.restype = C.c_int
+    lib.ncb_decoder_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.ncb_decoder_create.restype = C.c_int
+    lib.ncb_decoder_destroy.argtypes = [vp]
+    lib.ncb_decoder_destroy.restype = None
+    lib.ncb_decoder_last_error.argtypes = [vp]
+    lib.ncb_decoder_last_error.restype = C.c_char_p
+    lib.ncb_decoder_stage.argtypes = [vp, C.c_int, i32, vp, vp, i32, vp, vp, C.c_int]
+    lib.ncb_decoder_stage.restype = C.c_int
+    lib.ncb_decoder_launch.argtypes = [vp, C.c_int, i32, i32, i32, C.c_double, C.POINTER(NcbBatch), vp]
+    lib.ncb_decoder_launch.restype = C.c_int
+    lib.ncb_decoder_collect.argtypes = [vp, C.c_int, vp, vp, C.POINTER(i64)]
+    lib.ncb_decoder_collect.restype = C.c_int
+    lib.ncb_decoder_staged_bytes.argtypes = [vp, C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    lib.ncb_decoder_staged_bytes.restype = i64
+    lib.ncb_decoder_kernel_launches.argtypes = [vp, C.c_int]
+    lib.ncb_decoder_kernel_launches.restype = i64
+    lib.ncb_decoder_download.argtypes = [vp, C.c_int, vp, vp, vp, i64, i32]
+    lib.ncb_decoder_download.restype = C.c_int
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
     _libs[path] = lib

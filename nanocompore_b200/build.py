@@ -20,8 +20,9 @@ INCLUDE = os.path.join(ROOT, 'include')
 OBJDIR = os.path.join(ROOT, 'build', 'ncb')
 LIB = os.path.join(HERE, 'libncb.so')
 
-SOURCES = ['position_kernel.cu', 'gmm_split.cu', 'ks_pvalue.cu', 'fdr.cu', 'context.cu', 'api.cu', 'pack.cu', 'reader.cu']
-HEADERS = [os.path.join(CSRC, h) for h in ('ncb_internal.h', 'ncb_math.cuh', 'group_ops.cuh', 'gmm_common.cuh')] + \
+SOURCES = ['position_kernel.cu', 'gmm_split.cu', 'ks_pvalue.cu', 'fdr.cu', 'context.cu', 'api.cu', 'pack.cu', 'reader.cu', 'decode.cu']
+HEADERS = [os.path.join(CSRC, h) for h in ('ncb_internal.h', 'ncb_math.cuh', 'group_ops.cuh', 'gmm_common.cuh', 'bam_internal.h',
+                                               'inflate_core.cuh', 'decode_core.cuh', 'decode_stage.h')] + \
           [os.path.join(INCLUDE, 'ncb.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

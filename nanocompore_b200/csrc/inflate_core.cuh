@@ -415,6 +415,9 @@ struct SerialWarp {
     NCB_HD bool any(int v) const { return v != 0; }
     NCB_HD void sync() const {}
     NCB_HD uint8_t load_out(const uint8_t *p) const { return *p; }
+    NCB_HD int64_t reduce_min(int64_t v) const { return v; }
+    NCB_HD int64_t reduce_max(int64_t v) const { return v; }
+    NCB_HD int reduce_add(int v) const { return v; }
 };
 
 }  // namespace ncb_inflate

@@ -368,6 +368,16 @@ class Engine:
             self._check(self.lib.ncb_wait(self._handle, s))
         return results
 
+    def compare_struct(self, batch_struct, results: Results, *, stream=None, wait=True):
+        """Runs the hot path on an ``ncb_batch`` that is already filled in (the device-resident batch
+        of ``ncb_decoder_launch``); ``results`` may live on the host or on the device."""
+        r = results.struct()
+        s = self._stream(stream)
+        self._check(self.lib.ncb_compare(self._handle, C.byref(batch_struct), C.byref(r), s))
+        if wait:
+            self._check(self.lib.ncb_wait(self._handle, s))
+        return results
+
     def compare_dense(self, data: torch.Tensor, labels: torch.Tensor, results: Results = None, *,
                       diagnostics=False, stream=None, wait=True):
         """Runs the hot path on the reference's dense tensor ``data`` (P, R, V) float32 with

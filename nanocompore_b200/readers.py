@@ -506,9 +506,11 @@ class TranscriptPipeline:
         res = self._comparator.compare_packed(batch, self._device,
                                               min_coverage=0 if pre_filtered else max(min_cov, 1))
         klen, _ = kit_geometry(conf.get_kit())
+        # the positions of a transcript are one contiguous run of the batch
+        starts = np.concatenate([[0], np.cumsum([r.n_positions for r in row_sets])]).astype(np.int64)
         for k, i in enumerate(live):
             t = transcripts[i]
-            sel = ptx == k
+            sel = slice(int(starts[k]), int(starts[k + 1]))
             status = res['status'][sel]
             if pre_filtered:
                 if masks[k] is not None:

@@ -89,7 +89,29 @@ def sample_rows(n, k, device=None):
     return (i * (n - 1)) // max(k - 1, 1)
 
 
-def fdr_columns(cols, bh, group=None):
+class _Stages:
+    """Wall-clock milliseconds per stage of ``fdr_columns`` when a dict is passed as ``timings`` (every
+    stage then ends with a device synchronisation: a diagnostic pass, not the timed one)."""
+
+    def __init__(self, timings, device):
+        import time
+        self.t, self.dev, self.clock = timings, device, time.perf_counter
+        self.last = self._now() if timings is not None else 0.0
+
+    def _now(self):
+        if self.dev.type == 'cuda':
+            torch.cuda.synchronize(self.dev)
+        return self.clock()
+
+    def mark(self, name):
+        if self.t is None:
+            return
+        now = self._now()
+        self.t[name] = self.t.get(name, 0.0) + (now - self.last) * 1000.0
+        self.last = now
+
+
+def fdr_columns(cols, bh, group=None, timings=None):
     """Benjamini-Hochberg q-values of p-value columns whose rows are spread over the ranks.
 
     ``cols``: float64 tensor [C, n_local], the columns of this rank's rows (NaN = not tested);
@@ -114,10 +136,12 @@ def fdr_columns(cols, bh, group=None):
     device = cols.device
     inf = float('inf')
     out = torch.full_like(cols, float('nan'))
+    st = _Stages(timings, device)
     for c in range(C):
         col = cols[c]
         rows = torch.nonzero(col == col).squeeze(1)          # rows that hold a number
         v = col[rows]
+        st.mark('select_rows')
         # splitters: FDR_SAMPLE numbers of every rank (evenly spaced rows; NaN where a rank has none)
         if v.numel():
             mine = v[sample_rows(v.numel(), FDR_SAMPLE, device)]
@@ -131,12 +155,14 @@ def fdr_columns(cols, bh, group=None):
             splitters = pooled[at]
         else:
             splitters = torch.zeros(world - 1, dtype=cols.dtype, device=device)
+        st.mark('splitters')
         # range of a value: the number of splitters below it (equal values: one range)
         dest = torch.bucketize(v, splitters).to(torch.uint8 if world <= 256 else torch.int32)
         order = torch.argsort(dest, stable=True)
         send = v[order]
         rows = rows[order]
         counts = torch.bincount(dest.long(), minlength=world)
+        st.mark('partition')
         table = torch.empty((world, world), dtype=torch.int64, device=device)    # [source, range]
         dist.all_gather_into_tensor(table.view(-1), counts, group=group)
         table = table.cpu()
@@ -147,17 +173,23 @@ def fdr_columns(cols, bh, group=None):
         if total == 0:
             continue                                          # the same decision on every rank
         above = int(per_range[rank + 1:].sum())
+        st.mark('count_table')
         recv = torch.empty(sum(recv_split), dtype=cols.dtype, device=device)
         dist.all_to_all_single(recv, send, recv_split, send_split, group=group)
+        st.mark('all_to_all_values')
         q = bh(recv, above=above, total=total) if recv.numel() else recv
+        st.mark('sort_scan')
         low = q.min().reshape(1) if q.numel() else torch.full((1,), inf, dtype=cols.dtype, device=device)
         lows = torch.empty(world, dtype=cols.dtype, device=device)
         dist.all_gather_into_tensor(lows, low, group=group)
         if rank + 1 < world and q.numel():
             q = torch.clamp(q, max=lows[rank + 1:].min())     # running minimum over the ranges above
         back = torch.empty(sum(send_split), dtype=cols.dtype, device=device)
+        st.mark('range_minima')
         dist.all_to_all_single(back, q.contiguous(), send_split, recv_split, group=group)
+        st.mark('all_to_all_q')
         out[c, rows] = back
+        st.mark('scatter_rows')
     return out
 
 

@@ -93,7 +93,49 @@ def main():
                 "ms_per_transcript": {"read_select_pack": 1e3 * t_prepare, "compare_and_frames": 1e3 * t_finish,
                                       "stages": stages}}),
                 flush=True)
+            if kind == 'uncalled4_bam':
+                device_pipeline(cfg, reader, transcripts, args)
             reader.close()
+
+
+def device_pipeline(cfg, reader, transcripts, args):
+    """The same transcripts through DeviceTranscriptPipeline: compressed members up, decoding on the GPU."""
+    import torch
+    from nanocompore_b200.device_reader import DeviceTranscriptPipeline
+    for batch in sorted({args.batch, 4 * args.batch}):
+        pipe = DeviceTranscriptPipeline(cfg, reader, TranscriptComparator(cfg, Worker()), 'cuda:0')
+        list(pipe.run_stream(transcripts[:batch], batch_size=batch))             # warm-up: buffers, context
+        t0 = time.perf_counter()
+        rows = 0
+        for _, df in pipe.run_stream(transcripts, batch_size=batch):
+            rows += 0 if df is None else len(df)
+        total = time.perf_counter() - t0
+        tb = transcripts[:batch]
+        t0 = time.perf_counter()
+        prepared = pipe.prepare(tb)
+        t_stage = (time.perf_counter() - t0) / len(tb)
+        info = pipe._decoder.staged_bytes(prepared[1])
+        t0 = time.perf_counter()
+        pipe.finish(prepared)
+        t_finish = (time.perf_counter() - t0) / len(tb)
+        # the device half alone: upload + decode kernels, CUDA events
+        prepared = pipe.prepare(tb)
+        st = torch.cuda.Stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        pipe._decoder.launch(prepared[1], st, 0)
+        e1.record(st)
+        pipe._decoder.collect(prepared[1])
+        torch.cuda.synchronize()
+        ms_decode = e0.elapsed_time(e1) / len(tb)
+        print(json.dumps({
+            "format": "uncalled4_bam, device-side decoding", "transcripts": len(transcripts),
+            "positions_per_transcript": args.positions, "reads_per_transcript": args.reads, "host_cores": os.cpu_count(),
+            "batch": batch, "tested_positions": rows, "seconds": total, "tested_positions_per_s": rows / total,
+            "ms_per_transcript": {"stage_compressed_members": 1e3 * t_stage, "decode_compare_frames": 1e3 * t_finish,
+                                  "upload_and_decode_kernels": ms_decode},
+            "staged_per_batch": info}), flush=True)
+        pipe.close()
 
 
 if __name__ == '__main__':
