@@ -326,6 +326,96 @@ class TranscriptComparator:
             return None
         return self._assemble(transcript, positions, status, pv, st, counts, self._motor_dwell_offset > 0)
 
+    def assemble_batch(self, transcripts, starts, keeps, res, kmer_len=None):
+        """Result frames of all transcripts of one batch: ``_assemble`` for every transcript, built as ONE
+        frame over the batch's rows and cut into per-transcript slices (25 columns inserted into a fresh
+        DataFrame cost ~1 ms per transcript, twice the kernels of the transcript; the batch frame costs
+        ~0.1 ms per transcript).  ``starts`` [n + 1]: first batch position of every transcript; ``keeps``:
+        per transcript the boolean mask of its tested positions; ``res``: the result columns of the batch
+        (``Results.numpy()``).  ``kmer_len``: adds the ``kmer`` column of run.py:461-463 for transcripts
+        with a sequence.  Returns ``[DataFrame | None]``; values, dtypes, column order, row labels, log
+        messages and errors are those of the per-transcript path (tests/test_assemble_host.py)."""
+        with_motor = self._motor_dwell_offset > 0
+        methods = list(self._config.get_comparison_methods())
+        seqs = [getattr(t, 'seq', None) for t in transcripts]
+        with_kmer = kmer_len is not None and any(seqs)
+        if 'auto' in methods or (with_kmer and not all(seqs)):
+            # the incremental merge of the ``auto`` method (and a batch where only some transcripts
+            # carry a sequence) goes transcript by transcript
+            out = []
+            for k, t in enumerate(transcripts):
+                a, b = int(starts[k]), int(starts[k + 1])
+                keep = np.asarray(keeps[k], dtype=bool)
+                positions = np.nonzero(keep)[0]
+                frame = None
+                if positions.size:
+                    frame = self.assemble(t, positions.astype(np.int16), res['status'][a:b][keep],
+                                          res['pvalues'][:, a:b][:, keep], res['stats'][:, a:b][:, keep],
+                                          res['counts'][:, :, a:b][:, :, keep])
+                if frame is not None and kmer_len is not None and seqs[k]:
+                    from nanocompore_b200.readers import encode_kmers
+                    frame['kmer'] = encode_kmers(seqs[k], frame.pos.to_numpy(), kmer_len)
+                out.append(frame)
+            return out
+
+        n_tx = len(transcripts)
+        pos_list = [np.nonzero(np.asarray(k, dtype=bool))[0] for k in keeps]
+        n_sel = np.array([p.size for p in pos_list], dtype=np.int64)
+        if n_tx == 0 or n_sel.sum() == 0:
+            return [None] * n_tx
+        rows = np.concatenate([p + int(s) for p, s in zip(pos_list, starts[:n_tx])])
+        pos = np.concatenate(pos_list).astype(np.int16)
+        labels = np.concatenate([np.arange(p.size) for p in pos_list])   # row labels of the unfiltered frames
+        seg = np.repeat(np.arange(n_tx), n_sel)
+        status = res['status'][rows]
+        too_many = (status & L.NCB_POS_TOO_MANY_READS) != 0
+        if too_many.any():
+            name = transcripts[int(seg[np.nonzero(too_many)[0][0]])].name
+            raise NanocomporeError(
+                f"A position of transcript {name} has more than {L.NCB_MAX_READS} reads; "
+                "lower downsample_high_coverage")
+        bad_stds = (status & L.NCB_POS_BAD_STD) != 0                     # comparisons.py:108-120
+        if bad_stds.any():
+            for k in np.unique(seg[bad_stds]):
+                self._worker.log(
+                    "warning",
+                    "The standard deviation cannot be calculated for some positions on "
+                    f"transcript {transcripts[int(k)].name}, but are required for scaling the data. "
+                    f"The positions {pos[(seg == k) & bad_stds].tolist()} will be skipped.")
+            good = ~bad_stds
+            rows, pos, labels, seg, status = rows[good], pos[good], labels[good], seg[good], status[good]
+        n_rows = np.bincount(seg, minlength=n_tx)
+        ends = np.cumsum(n_rows)
+        ids = [t.id for t in transcripts]
+        columns = {'transcript_id': np.repeat(np.array(ids), n_rows) if rows.size else np.full(0, ids[0]),
+                   'pos': pos}
+        pv, st, counts = res['pvalues'][:, rows], res['stats'][:, rows], res['counts'][:, :, rows]
+        for column, row in shift_columns(with_motor):
+            columns[column] = st[row]
+        skipped = (status & L.NCB_POS_MW_EXACT_SKIPPED) != 0
+        if skipped.any() and any(m.upper() == 'MW' for m in methods):
+            for k in np.unique(seg[skipped]):
+                self._worker.log("error", "Error in nonparametric test: exact Mann-Whitney "
+                                 f"distribution too large on transcript {transcripts[int(k)].name}")
+        quiet = status & ~np.int32(L.NCB_POS_MW_EXACT_SKIPPED)
+        for test in self._get_test_masks(None, rows.size):
+            columns.update(self._test_columns(test, pv, st, counts, quiet, None))
+        context = self._config.get_sequence_context()
+        if context > 0:
+            tests = [col for col in columns if 'pvalue' in col]
+            live = n_rows > 0
+            offsets = np.concatenate([[0], ends[live]])
+            combined = self._combine_context(pos, [columns[test] for test in tests], offsets)
+            for test, values in zip(tests, combined):
+                columns[f"{test}_context_{context}"] = values
+        if with_kmer:
+            from nanocompore_b200.readers import encode_kmers
+            columns['kmer'] = np.concatenate([encode_kmers(seqs[k], pos[ends[k] - n_rows[k]:ends[k]], kmer_len)
+                                              for k in range(n_tx)])
+        table = pd.DataFrame(columns, index=labels, copy=False)
+        return [None if n_sel[k] == 0 else table.iloc[int(ends[k] - n_rows[k]):int(ends[k])]
+                for k in range(n_tx)]
+
     def _assemble(self, transcript, positions, status, pv, st, counts, with_motor):
         """Result frame of one transcript from its slice of the result columns
         (comparisons.py:83-84, 108-148, 204-215).  Without the ``auto`` method every test covers
@@ -442,7 +532,7 @@ class TranscriptComparator:
     def _combine_context_pvalues(self, results, test):
         return self._combine_context(results.pos.to_numpy(), [results[test].to_numpy(dtype=float)])[0]
 
-    def _combine_context(self, pos, columns):
+    def _combine_context(self, pos, columns, tx_offsets=None):
         """comparisons.py:436-474 for every p-value column of the transcript in one
         ``ncb_context_combine`` call: dense track, correlation of the track with
         its shifts, Hou's combination per row -- all in the context kernel.  Where the reference
@@ -460,7 +550,8 @@ class TranscriptComparator:
             raise NanocomporeError(f"sequence_context {context} is larger than NCB_CTX_MAX = {L.NCB_CTX_MAX}")
         pos = np.asarray(pos).astype(np.int64)
         pvalues = np.stack([np.asarray(c, dtype=np.float64) for c in columns])
-        combined, status = self._context_engine.context_combine([0, pos.size], pos, pvalues, context, weights)
+        combined, status = self._context_engine.context_combine(
+            [0, pos.size] if tx_offsets is None else tx_offsets, pos, pvalues, context, weights)
         if (status == L.NCB_CTX_TOO_SHORT).any():
             raise RuntimeError("Not enough p-values for a context of order %s" % context)
         if (status == L.NCB_CTX_INVALID_PVALUE).any():

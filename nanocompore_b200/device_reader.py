@@ -127,11 +127,13 @@ class DeviceTranscriptPipeline(TranscriptPipeline):
     """``TranscriptPipeline`` with the Uncalled4 decoding on the GPU (module docstring).  Same interface:
     ``run`` / ``run_stream`` return ``[(transcript, DataFrame | None)]`` in the order given."""
 
-    def __init__(self, config, reader, comparator, device='cuda:0', log=None, n_slots=2):
+    def __init__(self, config, reader, comparator, device='cuda:0', log=None, n_slots=3):
         super().__init__(config, reader, comparator, device, log)
         dev = torch.device(device)
         self._index = dev.index if dev.index is not None else 0
-        self._decoder = DeviceDecoder(config, reader, self._index, n_slots)
+        # three slots: batch k + 1 is staged while batch k runs on the GPU and the frames of batch
+        # k - 1 are read out of its result buffers (run_stream)
+        self._decoder = DeviceDecoder(config, reader, self._index, max(int(n_slots), 3))
         self._next_slot = 0
         self._results = {}           # pinned result buffers, by slot
         self._stream = torch.cuda.Stream(device=dev)
@@ -158,17 +160,17 @@ class DeviceTranscriptPipeline(TranscriptPipeline):
         host_part = super().prepare([transcripts[i] for i in on_host]) if on_host else None
         return transcripts, slot, on_device, on_host, host_part
 
-    def finish(self, prepared):
+    def launch(self, prepared):
+        """Enqueues the device half of a prepared batch -- upload of the compressed members, decode
+        kernels, ``ncb_compare``, results to pinned memory -- on the pipeline's stream and returns
+        without waiting."""
         transcripts, slot, on_device, on_host, host_part = prepared
         conf = self._conf
-        out = [(t, None) for t in transcripts]
-        redo = []
+        view, done, starts = None, None, np.zeros(1, dtype=np.int64)
         if on_device:
-            offset = conf.get_motor_dwell_offset()
             lens = np.array([transcripts[i].length for i in on_device], dtype=np.int64)
             starts = np.concatenate([[0], np.cumsum(lens)])
             P = int(starts[-1])
-            res, flags = None, np.zeros(len(on_device), dtype=np.int32)
             if P > 0:
                 engine = self._comparator._engine(self._device)
                 buf = self._results.get(slot)
@@ -178,33 +180,36 @@ class DeviceTranscriptPipeline(TranscriptPipeline):
                 view = buf.carve(P)
                 engine.configure(min_coverage=max(conf.get_min_coverage(), 1), dwell_is_raw=True)
                 try:
-                    batch = self._decoder.launch(slot, self._stream, offset)
-                    engine.compare_struct(batch, view, stream=self._stream, wait=True)
+                    batch = self._decoder.launch(slot, self._stream, conf.get_motor_dwell_offset())
+                    engine.compare_struct(batch, view, stream=self._stream, wait=False)
                 finally:
                     engine.configure(min_coverage=0, dwell_is_raw=False)
-                flags, reads, _ = self._decoder.collect(slot)
-                res = view.numpy()
+                done = torch.cuda.Event()
+                done.record(self._stream)
+        return prepared, view, done, starts
+
+    def collect(self, launched):
+        """Waits for a launched batch and assembles its frames."""
+        (transcripts, slot, on_device, on_host, host_part), view, done, starts = launched
+        conf = self._conf
+        out = [(t, None) for t in transcripts]
+        redo = []
+        if on_device and view is not None:
+            done.synchronize()
+            flags, _, _ = self._decoder.collect(slot)
+            res = view.numpy()
             klen, _ = kit_geometry(conf.get_kit())
+            ok = flags == L.NCB_DECODE_OK
+            redo = [i for k, i in enumerate(on_device) if not ok[k]]
+            # transcripts the decoder flagged keep no row here (the host path redoes them below)
+            keeps = [((res['status'][int(starts[k]):int(starts[k + 1])] & L.NCB_POS_LOW_COVERAGE) == 0)
+                     if ok[k] else np.zeros(int(starts[k + 1] - starts[k]), dtype=bool)
+                     for k in range(len(on_device))]
+            frames = self._comparator.assemble_batch([transcripts[i] for i in on_device], starts, keeps, res,
+                                                     kmer_len=klen)
             for k, i in enumerate(on_device):
-                t = transcripts[i]
-                if flags[k] != L.NCB_DECODE_OK:
-                    redo.append(i)
-                    continue
-                a, b = int(starts[k]), int(starts[k + 1])
-                if res is None or b == a:
-                    continue
-                status = res['status'][a:b]
-                keep = (status & L.NCB_POS_LOW_COVERAGE) == 0
-                positions = np.nonzero(keep)[0]
-                if positions.size == 0:
-                    continue
-                frame = self._comparator.assemble(t, positions.astype(np.int16), status[keep],
-                                                  res['pvalues'][:, a:b][:, keep], res['stats'][:, a:b][:, keep],
-                                                  res['counts'][:, :, a:b][:, :, keep])
-                seq = getattr(t, 'seq', None)
-                if frame is not None and seq:
-                    frame['kmer'] = encode_kmers(seq, frame.pos.to_numpy(), klen)       # run.py:461-463
-                out[i] = (t, frame)
+                if ok[k]:
+                    out[i] = (transcripts[i], frames[k])
         if host_part is not None:
             for i, item in zip(on_host, super().finish(host_part)):
                 out[i] = item
@@ -212,3 +217,28 @@ class DeviceTranscriptPipeline(TranscriptPipeline):
         for i in redo:
             out[i] = super().finish(super().prepare([transcripts[i]]))[0]
         return out
+
+    def finish(self, prepared):
+        return self.collect(self.launch(prepared))
+
+    def run_stream(self, transcripts, batch_size=64):
+        """``TranscriptPipeline.run_stream`` as a three-stage pipeline: a host thread stages the compressed
+        members of batch k + 1, the GPU decodes and compares batch k, and this thread assembles the frames
+        of batch k - 1 -- the GPU is never idle behind pandas.  Larger batches than the host path's: one
+        BGZF member is one warp of the inflate kernel, and a batch of 64 transcripts x 400 reads is
+        ~2 400 members for 148 SMs."""
+        from concurrent.futures import ThreadPoolExecutor as Pool
+        batches = [transcripts[i:i + batch_size] for i in range(0, len(transcripts), batch_size)]
+        if not batches:
+            return
+        with Pool(max_workers=1) as ex:
+            pending = ex.submit(self.prepare, batches[0])
+            in_flight = None
+            for nxt in batches[1:] + [None]:
+                prepared = pending.result()
+                pending = ex.submit(self.prepare, nxt) if nxt is not None else None
+                launched = self.launch(prepared)
+                if in_flight is not None:
+                    yield from self.collect(in_flight)
+                in_flight = launched
+            yield from self.collect(in_flight)

@@ -508,10 +508,8 @@ class TranscriptPipeline:
         klen, _ = kit_geometry(conf.get_kit())
         # the positions of a transcript are one contiguous run of the batch
         starts = np.concatenate([[0], np.cumsum([r.n_positions for r in row_sets])]).astype(np.int64)
+        keeps = []
         for k, i in enumerate(live):
-            t = transcripts[i]
-            sel = slice(int(starts[k]), int(starts[k + 1]))
-            status = res['status'][sel]
             if pre_filtered:
                 if masks[k] is not None:
                     keep = masks[k]
@@ -519,17 +517,12 @@ class TranscriptPipeline:
                     c0, c1 = coverage(row_sets[k])
                     keep = (c0 >= min_cov) & (c1 >= min_cov) & ((c0 + c1) > 0)
             else:
-                keep = (status & L.NCB_POS_LOW_COVERAGE) == 0
-            positions = np.nonzero(keep)[0]
-            if positions.size == 0:
-                continue
-            frame = self._comparator.assemble(t, positions.astype(np.int16), status[keep],
-                                              res['pvalues'][:, sel][:, keep], res['stats'][:, sel][:, keep],
-                                              res['counts'][:, :, sel][:, :, keep])
-            seq = getattr(t, 'seq', None)
-            if frame is not None and seq:
-                frame['kmer'] = encode_kmers(seq, frame.pos.to_numpy(), klen)       # run.py:461-463
-            out[i] = (t, frame)
+                keep = (res['status'][int(starts[k]):int(starts[k + 1])] & L.NCB_POS_LOW_COVERAGE) == 0
+            keeps.append(keep)
+        # one frame over the batch's rows, cut per transcript (comparisons.assemble_batch)
+        frames = self._comparator.assemble_batch([transcripts[i] for i in live], starts, keeps, res, kmer_len=klen)
+        for i, frame in zip(live, frames):
+            out[i] = (transcripts[i], frame)
         return out
 
     def run(self, transcripts):

@@ -43,6 +43,8 @@ def main():
     ap.add_argument('--positions', type=int, default=2000)
     ap.add_argument('--transcripts', type=int, default=24)
     ap.add_argument('--batch', type=int, default=8)
+    ap.add_argument('--repeat', type=int, default=16, help='device path: the task list is the transcripts this many times')
+    ap.add_argument('--device-batches', type=int, nargs='+', default=[32, 64, 128])
     args = ap.parse_args()
     rng = np.random.default_rng(5)
     with tempfile.TemporaryDirectory() as tmp:
@@ -99,26 +101,36 @@ def main():
 
 
 def device_pipeline(cfg, reader, transcripts, args):
-    """The same transcripts through DeviceTranscriptPipeline: compressed members up, decoding on the GPU."""
+    """The same files through DeviceTranscriptPipeline: compressed members up, decoding on the GPU, three
+    batches in flight (stage / GPU / frames).  The task list is the transcripts ``--repeat`` times over
+    (writing more distinct synthetic files costs 0.8 s each; nothing is cached between tasks: every task
+    stages, uploads, inflates and decodes its members again)."""
     import torch
     from nanocompore_b200.device_reader import DeviceTranscriptPipeline
-    for batch in sorted({args.batch, 4 * args.batch}):
+    tasks = transcripts * args.repeat
+    for batch in args.device_batches:
         pipe = DeviceTranscriptPipeline(cfg, reader, TranscriptComparator(cfg, Worker()), 'cuda:0')
-        list(pipe.run_stream(transcripts[:batch], batch_size=batch))             # warm-up: buffers, context
+        list(pipe.run_stream(tasks[:3 * batch], batch_size=batch))             # warm-up: buffers of every slot
         t0 = time.perf_counter()
         rows = 0
-        for _, df in pipe.run_stream(transcripts, batch_size=batch):
+        for _, df in pipe.run_stream(tasks, batch_size=batch):
             rows += 0 if df is None else len(df)
         total = time.perf_counter() - t0
-        tb = transcripts[:batch]
+        tb = tasks[:batch]
         t0 = time.perf_counter()
         prepared = pipe.prepare(tb)
         t_stage = (time.perf_counter() - t0) / len(tb)
         info = pipe._decoder.staged_bytes(prepared[1])
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pipe.finish(prepared)
-        t_finish = (time.perf_counter() - t0) / len(tb)
-        # the device half alone: upload + decode kernels, CUDA events
+        launched = pipe.launch(prepared)
+        t_launch = (time.perf_counter() - t0) / len(tb)
+        launched[2].synchronize()
+        t_gpu = (time.perf_counter() - t0) / len(tb)
+        t0 = time.perf_counter()
+        pipe.collect(launched)
+        t_frames = (time.perf_counter() - t0) / len(tb)
+        # the decode kernels alone: upload + kernels, CUDA events
         prepared = pipe.prepare(tb)
         st = torch.cuda.Stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -129,11 +141,14 @@ def device_pipeline(cfg, reader, transcripts, args):
         torch.cuda.synchronize()
         ms_decode = e0.elapsed_time(e1) / len(tb)
         print(json.dumps({
-            "format": "uncalled4_bam, device-side decoding", "transcripts": len(transcripts),
+            "format": "uncalled4_bam, device-side decoding", "transcripts": len(tasks),
+            "distinct_transcripts": len(transcripts),
             "positions_per_transcript": args.positions, "reads_per_transcript": args.reads, "host_cores": os.cpu_count(),
             "batch": batch, "tested_positions": rows, "seconds": total, "tested_positions_per_s": rows / total,
-            "ms_per_transcript": {"stage_compressed_members": 1e3 * t_stage, "decode_compare_frames": 1e3 * t_finish,
-                                  "upload_and_decode_kernels": ms_decode},
+            "ms_per_transcript": {"stage_compressed_members": 1e3 * t_stage, "launch_call": 1e3 * t_launch,
+                                  "upload_decode_compare": 1e3 * t_gpu, "frames": 1e3 * t_frames,
+                                  "upload_and_decode_kernels": ms_decode,
+                                  "whole_run": 1e3 * total / len(tasks)},
             "staged_per_batch": info}), flush=True)
         pipe.close()
 

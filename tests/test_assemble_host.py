@@ -112,3 +112,47 @@ def test_correction_method_is_checked_when_the_configuration_is_read():
         PathConfig(dict(base, correction_method='bonferroni'))
     with pytest.raises(ValueError, match='holm'):
         check_correction_method('holm')
+
+
+@pytest.mark.parametrize('methods', [['GMM', 'KS', 'MW'], ['auto'], ['KS']])
+def test_batch_frames_equal_the_per_transcript_frames(methods):
+    """``assemble_batch`` (one frame over the rows of a batch, cut per transcript) gives the frames, row
+    labels, dtypes, log messages and the kmer column of ``_assemble`` transcript by transcript."""
+    from nanocompore_b200.readers import encode_kmers
+    rng = np.random.default_rng(3)
+
+    class T:
+        def __init__(self, i, n):
+            self.id, self.name, self.length = 10 + i, f'tx{i}', n
+            self.seq = ''.join(rng.choice(list('ACGT'), n))
+
+    lens = [50, 1, 37, 80, 12]
+    txs = [T(i, n) for i, n in enumerate(lens)]
+    starts = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    P = int(starts[-1])
+    bad = [starts[0] + 4, starts[3] + 7, starts[3] + 8] + list(range(starts[4], starts[5]))   # tx4: every row
+    status, pv, st, counts = columns(P, rng, bad=bad, auto_gmm=range(0, P, 3))
+    status[starts[2] + 5] |= L.NCB_POS_MW_EXACT_SKIPPED
+    keeps = [rng.random(n) < 0.7 for n in lens]
+    keeps[1][:] = False                                   # a transcript with no tested position
+    keeps[4][:] = True
+    keeps[0][4] = keeps[3][7] = keeps[3][8] = keeps[2][5] = True
+    status[np.concatenate([~k for k in keeps])] |= L.NCB_POS_LOW_COVERAGE
+    res = {'status': status, 'pvalues': pv, 'stats': st, 'counts': counts}
+    cfg = PathConfig(dict(data=DATA, depleted_condition='kd', comparison_methods=methods))
+    w1, w2 = Worker(), Worker()
+    got = TranscriptComparator(cfg, w1).assemble_batch(txs, starts, keeps, res, kmer_len=5)
+    one = TranscriptComparator(cfg, w2)
+    for k, t in enumerate(txs):
+        a, b = starts[k], starts[k + 1]
+        positions = np.nonzero(keeps[k])[0]
+        want = one.assemble(t, positions.astype(np.int16), status[a:b][keeps[k]], pv[:, a:b][:, keeps[k]],
+                            st[:, a:b][:, keeps[k]], counts[:, :, a:b][:, :, keeps[k]])
+        if want is None:
+            assert got[k] is None
+            continue
+        want['kmer'] = encode_kmers(t.seq, want.pos.to_numpy(), 5)
+        pd.testing.assert_frame_equal(got[k], want, check_exact=True)
+    assert got[1] is None and len(got[4]) == 0 and len(got[0]) > 0
+    # the same messages (the batch logs all warnings of a kind together)
+    assert sorted(w1.messages) == sorted(w2.messages) and len(w1.messages) >= (3 if 'MW' in methods else 1)
