@@ -464,7 +464,7 @@ def run_gpu_arm(args):
     t_gen = time.perf_counter()
     for b in range(n_pool):
         txs = make_transcripts(20251019 + CONFIG_INDEX + 1000 * rank + b, T)
-        batch, _, _ = pack_csr([(t.data, t.samples, t.conditions) for t in txs], pin=True, wire='i16')
+        batch, _, _ = pack_csr([(t.data, t.samples, t.conditions) for t in txs], pin=True, wire='i16r')
         host_pool.append(batch)
         dev_pool.append(batch.to(dev))
         pool_tx0.append(txs[0])
@@ -658,6 +658,19 @@ def run_gpu_arm(args):
                "h2d_bytes_per_step": int(np.mean([b.nbytes() for b in f32_pool])) * B,
                "stage": "compare only (no correction / gather)", "ms_per_step": ms_f32 / K}
     del f32_pool
+    # the same int16 entries with a label byte each (NCB_LAYOUT_CSR_I16, 5 bytes per entry): what the label
+    # runs buy end to end
+    lab_pool = [CsrBatch(b.pos_offsets, b.signal, b.label, b.max_entries) for b in host_pool]
+    rig.end_to_end(lab_pool, order_w[:NSLOT * 2], res_host)
+    barrier()
+    t0 = time.perf_counter()
+    tested_lab = rig.end_to_end(lab_pool, order_k, res_host)
+    torch.cuda.synchronize(dev)
+    ms_lab = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+    e2e_lab = {"value": sum_over_ranks(float(tested_lab)) / (ms_lab / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": int(np.mean([b.nbytes() for b in lab_pool])) * B,
+               "stage": "compare only (no correction / gather)", "ms_per_step": ms_lab / K}
+    del lab_pool
 
     # ---- a FIXED job of the config-5 mix, LPT-sharded: strong scaling --------------------------
     job_skew = run_skew_job(args, rig, world, rank, dev, barrier, max_over_ranks, sum_over_ranks)
@@ -754,7 +767,7 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(T, B), "positions_per_step": P * B,
                    "tested_positions_per_step": tested_positions / K,
-                   "positions_per_batch": P, "reads_per_batch": entries, "wire": "int16 entries (NCB_LAYOUT_CSR_I16)",
+                   "positions_per_batch": P, "reads_per_batch": entries, "wire": "int16 entries + label runs per position (NCB_LAYOUT_CSR_I16_RUNS, 4 bytes per entry)",
                    "l2": f"inputs larger than L2: pool of {n_pool} distinct batches, consecutive launches read different batches",
                    "slots": NSLOT, "timed_region_s": ms_value / 1000.0,
                    "parallelism": f"transcript sharding x{world} (LPT over one global list), no data-path collective"},
@@ -768,6 +781,7 @@ def run_gpu_arm(args):
         "h2d": {"probe_all_ranks_copying": h2d_probe, "per_rank_GBps_in_the_compare_stage_of_the_job": e2e_h2d_GBps,
                 "share_of_probe": e2e_h2d_GBps / h2d_probe["per_rank_GBps"]},
         "e2e_f32_wire": e2e_f32,
+        "e2e_label_bytes_wire": e2e_lab,
         "em_fp32": dict(em_fp32, speedup_of_mixture_kernels=ms_gmm / em_fp32["ms_mixture_per_batch"]),
         "parity_spot_check": check,
         "gpu_launches": total_launches,
@@ -789,7 +803,7 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
-def pack_pool(tx_lists, dev, methods_wire='i16'):
+def pack_pool(tx_lists, dev, methods_wire='i16r'):
     from nanocompore_b200.engine import pack_csr
     host, devb = [], []
     for txs in tx_lists:
@@ -962,15 +976,15 @@ def run_skew_job(args, rig, world, rank, dev, barrier, max_over_ranks, sum_over_
         if reads[t] == 5000:
             tx = heavy_pool[n_h % 2]
             n_h += 1
-            batches.append(pack_csr([(tx.data, tx.samples, tx.conditions)], pin=True, wire='i16')[0])
+            batches.append(pack_csr([(tx.data, tx.samples, tx.conditions)], pin=True, wire='i16r')[0])
         else:
             tx = make_transcript(np.random.default_rng(5200 + int(t)), 1000, int(reads[t]), uncalled4=True)
             tail_items.append((tx.data, tx.samples, tx.conditions))
             if len(tail_items) == 25:
-                batches.append(pack_csr(tail_items, pin=True, wire='i16')[0])
+                batches.append(pack_csr(tail_items, pin=True, wire='i16r')[0])
                 tail_items = []
     if tail_items:
-        batches.append(pack_csr(tail_items, pin=True, wire='i16')[0])
+        batches.append(pack_csr(tail_items, pin=True, wire='i16r')[0])
     t_gen = time.perf_counter() - t_gen
     # heavy batches first: the long ones do not form the tail of the job
     batches.sort(key=lambda b: -b.n_entries)

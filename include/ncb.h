@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NCB_ABI_VERSION 2
+#define NCB_ABI_VERSION 3
 
 typedef struct ncb_handle ncb_handle;
 
@@ -70,12 +70,23 @@ enum { NCB_MEM_HOST = 0, NCB_MEM_DEVICE = 1 };
 enum {
     NCB_LAYOUT_CSR = 0,   /* ragged: pos_offsets[P+1], signal float32[E][V], label[E]     */
     NCB_LAYOUT_DENSE = 1, /* the reference's tensor: signal[P][R][V] with NaN, label[R]   */
-    NCB_LAYOUT_CSR_I16 = 2 /* ragged like NCB_LAYOUT_CSR with the entries as int16 codes: signal points at
+    NCB_LAYOUT_CSR_I16 = 2, /* ragged like NCB_LAYOUT_CSR with the entries as int16 codes: signal points at
                              int16[E][V], value = (float)code, -32768 = NaN.  This is what Uncalled4 stores
                              (tags uc / ul are int16 arrays copied into the float32 tensor as they are,
                              uncalled4.py:118-192, -32768 -> NaN at 103-107), so for that input the layout is
                              lossless at 5 instead of 9 bytes per entry on the host-to-device link          */
+    NCB_LAYOUT_CSR_I16_RUNS = 3 /* NCB_LAYOUT_CSR_I16 without the label byte of every entry: the reference
+                             concatenates the reads of a transcript sample after sample (run.py:820-826), so
+                             the entries of a position are RUNS of equal labels in one fixed order.
+                             ncb_batch.run_labels[n_runs] (host memory, whatever ncb_batch.memory says) names
+                             the label of every run, and ncb_batch.label points at uint16 run_ends[P][n_runs]:
+                             entry e of position p (0-based inside the position) belongs to the first run j
+                             with e < run_ends[p][j]; run_ends[p] is non-decreasing and its last element is
+                             the number of entries of the position.  4 bytes per entry on the link; the
+                             label bytes are rebuilt on the device (one small kernel) before the statistics
+                             kernel.  ncb_pack_label_runs writes run_ends from per-entry labels               */
 };
+#define NCB_MAX_RUNS 16
 
 /* per-position status bits; the row is dropped by the host mirror when
  * (status & NCB_POS_DROP_MASK) != 0 */
@@ -139,6 +150,9 @@ typedef struct {
                                    exceeds it gets NCB_POS_TOO_MANY_READS                                */
     int32_t n_vars;             /* V: 2, or 3 with the motor-dwell column of
                                    Worker._prepare_data (run.py:575-584); CSR: 0 means 2  */
+    const uint8_t *run_labels;  /* NCB_LAYOUT_CSR_I16_RUNS: [n_runs] label of every run, HOST memory; else NULL */
+    int32_t n_runs;             /* NCB_LAYOUT_CSR_I16_RUNS: 1..NCB_MAX_RUNS; else 0       */
+    int32_t reserved;           /* 0                                                      */
 } ncb_batch;
 
 /* rows of ncb_results.pvalues ([NCB_PV_ROWS][P], float64, NaN = not tested) */
@@ -334,6 +348,12 @@ int ncb_pack_rows_fill_i16(const float *const *intensity, const float *const *dw
                            const uint8_t *row_label, int64_t n_rows, int64_t n_positions,
                            int32_t motor_offset, const int64_t *pos_offsets, int16_t *signal_out,
                            uint8_t *label_out, int threads);
+/* Label runs of a packed CSR batch (NCB_LAYOUT_CSR_I16_RUNS): run_ends[p][j] = the number of entries of
+ * position p whose label is one of run_labels[0..j].  NCB_ERR_INVALID when a label is not in run_labels, when
+ * the labels of a position do not come in the order of run_labels (the batch then travels with its label
+ * bytes), when a position has more than 65535 entries, or n_runs is not in 1..NCB_MAX_RUNS. */
+int ncb_pack_label_runs(const int64_t *pos_offsets, const uint8_t *label, int64_t n_positions,
+                        const uint8_t *run_labels, int32_t n_runs, uint16_t *run_ends, int threads);
 /* common.get_reads_invalid_ratio (common.py:298-329): per row, the share of positions between
  * its first and last valid intensity that are NaN; NaN for a row without any valid position. */
 int ncb_rows_invalid_ratio(const float *const *intensity, int64_t n_rows, int64_t n_positions,

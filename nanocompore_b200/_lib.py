@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # NCB_LIB_PATH lets a tuning run load an experimental build of the same ABI
 LIB_PATH = os.environ.get('NCB_LIB_PATH') or os.path.join(HERE, 'libncb.so')
 
-NCB_ABI_VERSION = 2
+NCB_ABI_VERSION = 3
 NCB_MAX_READS = 10240
 NCB_MAX_SAMPLES = 64
 
@@ -19,7 +19,8 @@ NCB_OK, NCB_ERR_INVALID, NCB_ERR_CUDA, NCB_ERR_NOMEM, NCB_ERR_TOO_MANY_READS = 0
 NCB_TEST_KS, NCB_TEST_MW, NCB_TEST_TT, NCB_TEST_GMM, NCB_TEST_LOGIT, NCB_TEST_AUTO = 1, 2, 4, 8, 16, 32
 NCB_COUNTS_NONE, NCB_COUNTS_HARD, NCB_COUNTS_SOFT = 0, 1, 2
 NCB_MEM_HOST, NCB_MEM_DEVICE = 0, 1
-NCB_LAYOUT_CSR, NCB_LAYOUT_DENSE, NCB_LAYOUT_CSR_I16 = 0, 1, 2
+NCB_LAYOUT_CSR, NCB_LAYOUT_DENSE, NCB_LAYOUT_CSR_I16, NCB_LAYOUT_CSR_I16_RUNS = 0, 1, 2, 3
+NCB_MAX_RUNS = 16
 
 NCB_POS_LOW_COVERAGE, NCB_POS_BAD_STD, NCB_POS_TOO_MANY_READS = 1, 2, 4
 NCB_POS_DROP_MASK = 7
@@ -49,7 +50,7 @@ NCB_DF_ROWS = 17
 
 EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_results_host_bytes',
-           'ncb_pack_fill_i16', 'ncb_pack_rows_fill_i16', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr', 'ncb_bh_fdr_segment',
+           'ncb_pack_fill_i16', 'ncb_pack_rows_fill_i16', 'ncb_pack_label_runs', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr', 'ncb_bh_fdr_segment',
            'ncb_context_combine',
            'ncb_kernel_launches', 'ncb_set_timing', 'ncb_last_timing', 'ncb_timing_totals', 'ncb_timing_mixture',
            'ncb_pack_count', 'ncb_pack_fill', 'ncb_pack_rows_count', 'ncb_pack_rows_fill',
@@ -74,7 +75,8 @@ class NcbOpts(C.Structure):
 class NcbBatch(C.Structure):
     _fields_ = [('layout', C.c_int32), ('memory', C.c_int32), ('n_positions', C.c_int64),
                 ('n_entries', C.c_int64), ('pos_offsets', C.c_void_p), ('signal', C.c_void_p),
-                ('label', C.c_void_p), ('n_reads', C.c_int32), ('n_vars', C.c_int32)]
+                ('label', C.c_void_p), ('n_reads', C.c_int32), ('n_vars', C.c_int32),
+                ('run_labels', C.c_void_p), ('n_runs', C.c_int32), ('reserved', C.c_int32)]
 
 
 class NcbResults(C.Structure):
@@ -145,6 +147,8 @@ def load(path=None):
     lib.ncb_pack_fill_i16.restype = C.c_int
     lib.ncb_pack_rows_fill_i16.argtypes = [vp, vp, vp, i64, i64, i32, vp, vp, vp, C.c_int]
     lib.ncb_pack_rows_fill_i16.restype = C.c_int
+    lib.ncb_pack_label_runs.argtypes = [vp, vp, i64, vp, i32, vp, C.c_int]
+    lib.ncb_pack_label_runs.restype = C.c_int
     lib.ncb_results_host_bytes.argtypes = [vp, i64, i32, C.c_int]
     lib.ncb_results_host_bytes.restype = i64
     lib.ncb_pack_rows_count.argtypes = [vp, vp, i64, i64, i32, vp, C.c_int]

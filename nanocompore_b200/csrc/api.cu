@@ -10,6 +10,29 @@
 
 int ncb_configure_ks_kernels(void);
 
+// NCB_LAYOUT_CSR_I16_RUNS: the label byte of every entry from the run ends of its position (include/ncb.h).
+// One warp per position: lane j holds run_ends[p][j], every lane labels the entries e = lane, lane + 32, ...
+struct NcbRunLabels { uint8_t v[NCB_MAX_RUNS]; };
+namespace ncb {
+__global__ void __launch_bounds__(256) expand_runs_kernel(const int64_t *__restrict__ pos_offsets,
+                                                          const uint16_t *__restrict__ run_ends, NcbRunLabels labels,
+                                                          int n_runs, int64_t n_positions, uint8_t *__restrict__ label) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n_positions; p += warps) {
+        const int64_t o = pos_offsets[p];
+        const int n = (int)(pos_offsets[p + 1] - o);
+        const int mine = lane < n_runs ? (int)run_ends[p * n_runs + lane] : 0x7fffffff;
+        for (int e = lane; e < ((n + 31) & ~31); e += 32) {
+            int run = 0;
+            for (int j = 0; j < n_runs - 1; ++j) run += e >= __shfl_sync(0xffffffffu, mine, j) ? 1 : 0;
+            if (e < n) label[o + e] = labels.v[run];
+        }
+    }
+}
+}  // namespace ncb
+
 struct DevBuf {
     void *ptr = nullptr;
     size_t bytes = 0;
@@ -35,7 +58,7 @@ struct ncb_handle {
     // cleared) by ncb_wait after the stream has drained
     int32_t *flag_host = nullptr, *flag_dev = nullptr;
     // grow-only device buffers
-    DevBuf in_signal, in_label, in_offsets;
+    DevBuf in_signal, in_label, in_offsets, in_runs;
     DevBuf out_status, out_pvalues, out_stats, out_counts, out_di, out_df;
     DevBuf ks_n0, ks_n1, ks_h, zbuf, gmm_n, gmm_rec, zbuf3, gmm_n3, mw_scratch;
     DevBuf wl_count, wl_list;
@@ -222,7 +245,7 @@ void ncb_destroy(ncb_handle *h) {
     DeviceGuard guard;
     guard.enter(h->device);
     DevBuf *all[] = {&h->in_signal, &h->in_label, &h->in_offsets, &h->out_status, &h->out_pvalues,
-                     &h->out_stats, &h->out_counts, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
+                     &h->out_stats, &h->out_counts, &h->in_runs, &h->out_di, &h->out_df, &h->ks_n0, &h->ks_n1,
                      &h->ks_h, &h->zbuf, &h->gmm_n, &h->gmm_rec, &h->mw_scratch, &h->zbuf3, &h->gmm_n3, &h->wl_count, &h->wl_list, &h->kw_hist, &h->kw_cursor, &h->kw_list,
                      &h->kw_bin, &h->kw_fetch, &h->kw_rtab, &h->fdr_scratch, &h->fdr_p, &h->fdr_q,
                      &h->unit_a, &h->unit_b, &h->unit_c, &h->unit_d,
@@ -263,8 +286,11 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     if (!res->status || !res->pvalues || !res->stats) return fail(h, NCB_ERR_INVALID, "ncb_compare: status, pvalues and stats are required");
     ON_DEVICE(h);
     const ncb_opts &o = h->opts;
-    const bool i16 = b->layout == NCB_LAYOUT_CSR_I16;
+    const bool runs = b->layout == NCB_LAYOUT_CSR_I16_RUNS;
+    const bool i16 = b->layout == NCB_LAYOUT_CSR_I16 || runs;
     const bool csr = b->layout == NCB_LAYOUT_CSR || i16;
+    if (runs && (b->n_runs < 1 || b->n_runs > NCB_MAX_RUNS || !b->run_labels))
+        return fail(h, NCB_ERR_INVALID, "ncb_compare: a label-run batch needs 1..NCB_MAX_RUNS run_labels");
     int64_t E;
     size_t label_bytes;
     int n_vars;
@@ -272,7 +298,7 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
         if (!b->pos_offsets) return fail(h, NCB_ERR_INVALID, "ncb_compare: CSR batch without pos_offsets");
         E = b->n_entries;
         if (E < 0) return fail(h, NCB_ERR_INVALID, "ncb_compare: negative n_entries");
-        label_bytes = (size_t)E;
+        label_bytes = runs ? (size_t)P * b->n_runs * sizeof(uint16_t) : (size_t)E;
         n_vars = b->n_vars == 0 ? 2 : b->n_vars;
         if (n_vars < 2 || n_vars > 3) return fail(h, NCB_ERR_INVALID, "ncb_compare: n_vars must be 2 or 3");
     } else if (b->layout == NCB_LAYOUT_DENSE) {
@@ -329,11 +355,12 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
     // ---- inputs ------------------------------------------------------------------------
     if (b->memory == NCB_MEM_HOST) {
         ENSURE(h->in_signal, signal_bytes);
-        ENSURE(h->in_label, label_bytes);
+        DevBuf &lab_in = runs ? h->in_runs : h->in_label;
+        ENSURE(lab_in, label_bytes);
         if (signal_bytes) CK(cudaMemcpyAsync(h->in_signal.ptr, b->signal, signal_bytes, cudaMemcpyHostToDevice, s));
-        if (label_bytes) CK(cudaMemcpyAsync(h->in_label.ptr, b->label, label_bytes, cudaMemcpyHostToDevice, s));
+        if (label_bytes) CK(cudaMemcpyAsync(lab_in.ptr, b->label, label_bytes, cudaMemcpyHostToDevice, s));
         a.signal = (const float *)h->in_signal.ptr;
-        a.label = (const uint8_t *)h->in_label.ptr;
+        a.label = (const uint8_t *)lab_in.ptr;
         if (csr) {
             ENSURE(h->in_offsets, (size_t)(P + 1) * sizeof(int64_t));
             CK(cudaMemcpyAsync(h->in_offsets.ptr, b->pos_offsets, (size_t)(P + 1) * sizeof(int64_t),
@@ -346,6 +373,20 @@ int ncb_compare(ncb_handle *h, const ncb_batch *b, ncb_results *res, void *strea
         a.pos_offsets = csr ? b->pos_offsets : nullptr;
     } else {
         return fail(h, NCB_ERR_INVALID, "ncb_compare: unknown batch memory kind");
+    }
+    if (runs) {
+        // label bytes of the entries from the run ends (device to device: nothing more crosses the link)
+        ENSURE(h->in_label, (size_t)(E > 0 ? E : 1));
+        NcbRunLabels rl;
+        memset(&rl, 0, sizeof(rl));
+        memcpy(rl.v, b->run_labels, (size_t)b->n_runs);
+        const int64_t want = (P + 7) / 8;                       // 8 warps per CTA, one position per warp and trip
+        const int grid = (int)(want < (int64_t)h->sm_count * 8 ? (want > 0 ? want : 1) : (int64_t)h->sm_count * 8);
+        ncb::expand_runs_kernel<<<grid, 256, 0, s>>>(a.pos_offsets, (const uint16_t *)a.label, rl, b->n_runs, P,
+                                                     (uint8_t *)h->in_label.ptr);
+        CK(cudaGetLastError());
+        ++h->launches;
+        a.label = (const uint8_t *)h->in_label.ptr;
     }
 
     // ---- outputs -----------------------------------------------------------------------

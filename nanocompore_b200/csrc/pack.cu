@@ -238,4 +238,37 @@ int ncb_pack_rows_fill_i16(const float *const *intensity, const float *const *dw
     return any_bad.load() ? NCB_ERR_INVALID : NCB_OK;
 }
 
+int ncb_pack_label_runs(const int64_t *pos_offsets, const uint8_t *label, int64_t n_positions,
+                        const uint8_t *run_labels, int32_t n_runs, uint16_t *run_ends, int threads) {
+    if (n_positions < 0 || n_runs < 1 || n_runs > NCB_MAX_RUNS || !run_labels ||
+        (n_positions > 0 && (!pos_offsets || !run_ends)))
+        return NCB_ERR_INVALID;
+    int16_t run_of[256];
+    for (int i = 0; i < 256; ++i) run_of[i] = -1;
+    for (int j = 0; j < n_runs; ++j) {
+        if (run_of[run_labels[j]] >= 0) return NCB_ERR_INVALID;   // a label names one run
+        run_of[run_labels[j]] = (int16_t)j;
+    }
+    const int16_t *lut = run_of;
+    std::atomic<int> any_bad(0);
+    std::atomic<int> *flag = &any_bad;
+    parallel_for(n_positions, threads, [=](int64_t lo, int64_t hi) {
+        bool bad = false;
+        for (int64_t p = lo; p < hi; ++p) {
+            const int64_t o = pos_offsets[p], n = pos_offsets[p + 1] - o;
+            uint16_t *ends = run_ends + p * (int64_t)n_runs;
+            if (n < 0 || n > 65535 || (n > 0 && !label)) { bad = true; for (int j = 0; j < n_runs; ++j) ends[j] = 0; continue; }
+            int run = 0;
+            for (int64_t e = 0; e < n; ++e) {
+                const int r = lut[label[o + e]];
+                if (r < run) { bad = true; break; }           // unknown label (-1) or out of order
+                while (run < r) ends[run++] = (uint16_t)e;
+            }
+            while (run < n_runs) ends[run++] = (uint16_t)n;
+        }
+        if (bad) flag->store(1);
+    });
+    return any_bad.load() ? NCB_ERR_INVALID : NCB_OK;
+}
+
 }  // extern "C"

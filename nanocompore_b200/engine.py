@@ -50,12 +50,17 @@ class CsrBatch:
     pos_offsets int64 [P+1]; signal [E, V] {intensity, dwell[, motor dwell]}, V = 2 or 3 -- float32
     (NCB_LAYOUT_CSR) or int16 codes (NCB_LAYOUT_CSR_I16: value = float(code), -32768 = NaN, the encoding
     of Uncalled4's tags, 5 instead of 9 bytes per entry on the host-to-device link); label uint8 [E].
+    With ``run_ends`` (uint16 [P, n_runs]) and ``run_labels`` (numpy uint8 [n_runs]) an int16 batch travels
+    as NCB_LAYOUT_CSR_I16_RUNS: the reads of a position come sample after sample, so the label bytes are
+    rebuilt on the device from the run ends (4 bytes per entry on the link; ``label`` stays on the host).
     Tensors are either all pinned-host or all on the device."""
     pos_offsets: torch.Tensor
     signal: torch.Tensor
     label: torch.Tensor
     max_entries: int = 0      # most entries a position has, if the packer knows (0 = unknown): the
                               # size classes above it are not launched (ncb_batch.n_reads)
+    run_ends: torch.Tensor = None
+    run_labels: np.ndarray = None
 
     @property
     def n_positions(self):
@@ -66,11 +71,42 @@ class CsrBatch:
         return self.signal.shape[0]
 
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.pos_offsets, self.signal, self.label))
+        """Bytes ``ncb_compare`` copies to the device for this batch."""
+        last = self.run_ends if self.run_ends is not None else self.label
+        return sum(t.numel() * t.element_size() for t in (self.pos_offsets, self.signal, last))
 
     @property
     def wire(self):
+        if self.run_ends is not None:
+            return 'i16r'
         return 'i16' if self.signal.dtype == torch.int16 else 'f32'
+
+    def with_label_runs(self, threads=None):
+        """This int16 batch with the run ends of its labels (NCB_LAYOUT_CSR_I16_RUNS), or None when the
+        labels of a position do not come as runs in one common order (such a batch keeps its label bytes)."""
+        import os
+        if self.signal.dtype != torch.int16 or self.signal.is_cuda:
+            raise ValueError("label runs are built for int16 batches on the host")
+        lab = self.label.numpy()
+        # run order: ascending sample id (the reference concatenates the samples in config order,
+        # run.py:820-826, which is the order of their ids), else the order of the labels' first entries
+        present, first = np.unique(lab, return_index=True)
+        if present.size < 1 or present.size > L.NCB_MAX_RUNS:
+            return None
+        P = self.n_positions
+        ends = torch.empty((P, present.size), dtype=torch.uint16, pin_memory=self.signal.is_pinned())
+        by_first = present[np.argsort(first, kind='stable')]
+        orders = [present] if np.array_equal(present, by_first) else [present, by_first]
+        for order in orders:
+            run_labels = np.ascontiguousarray(order, dtype=np.uint8)
+            rc = L.load().ncb_pack_label_runs(self.pos_offsets.data_ptr(), self.label.data_ptr(), P,
+                                              run_labels.ctypes.data, run_labels.size, ends.data_ptr(),
+                                              threads or min(16, os.cpu_count() or 1))
+            if rc == L.NCB_OK:
+                break
+        else:
+            return None
+        return CsrBatch(self.pos_offsets, self.signal, self.label, self.max_entries, ends, run_labels)
 
     def signal_f32(self):
         """The entries as float32 numbers whatever the wire format (int16 code -32768 = NaN)."""
@@ -83,11 +119,14 @@ class CsrBatch:
     def to(self, device, non_blocking=False):
         return CsrBatch(self.pos_offsets.to(device, non_blocking=non_blocking),
                         self.signal.to(device, non_blocking=non_blocking),
-                        self.label.to(device, non_blocking=non_blocking), self.max_entries)
+                        self.label.to(device, non_blocking=non_blocking), self.max_entries,
+                        None if self.run_ends is None else self.run_ends.to(device, non_blocking=non_blocking),
+                        self.run_labels)
 
     def pin(self):
         return CsrBatch(self.pos_offsets.pin_memory(), self.signal.pin_memory(), self.label.pin_memory(),
-                        self.max_entries)
+                        self.max_entries, None if self.run_ends is None else self.run_ends.pin_memory(),
+                        self.run_labels)
 
 
 def pack_csr(transcripts, pin=False, threads=None, wire='f32'):
@@ -95,8 +134,9 @@ def pack_csr(transcripts, pin=False, threads=None, wire='f32'):
     (ncb_pack_count / ncb_pack_fill, multi-threaded C++).
 
     ``wire``: 'f32' -> float32 entries; 'i16' -> int16 entries (every number of the tensors must be an
-    integer in [-32767, 32767], as in Uncalled4 input: ValueError otherwise); 'auto' -> int16 when
-    the data allows it, else float32.
+    integer in [-32767, 32767], as in Uncalled4 input: ValueError otherwise); 'i16r' -> int16 entries and
+    label runs instead of label bytes (``CsrBatch.with_label_runs``; label bytes when the reads are not
+    grouped by sample); 'auto' -> int16 when the data allows it, else float32.
 
     ``transcripts``: iterable of (data (P,R,V>=2) float32 with NaN, samples (R,), conditions (R,)).
     A read is kept at a position when any of its two variables is a number.  Read order inside
@@ -130,8 +170,9 @@ def pack_csr(transcripts, pin=False, threads=None, wire='f32'):
     if pin:
         t_off = t_off.pin_memory()
         offsets = t_off.numpy()
-    if wire not in ('f32', 'i16', 'auto'):
-        raise ValueError(f"wire must be 'f32', 'i16' or 'auto', not {wire!r}")
+    if wire not in ('f32', 'i16', 'i16r', 'auto'):
+        raise ValueError(f"wire must be 'f32', 'i16', 'i16r' or 'auto', not {wire!r}")
+    want_runs, wire = wire == 'i16r', 'i16' if wire == 'i16r' else wire
     t_lab = torch.empty((E,), dtype=torch.uint8, **kw)
     ptx = [np.full(d.shape[0], ti, dtype=np.int32) for ti, (d, _) in enumerate(items)]
     pidx = [np.arange(d.shape[0], dtype=np.int32) for d, _ in items]
@@ -157,6 +198,8 @@ def pack_csr(transcripts, pin=False, threads=None, wire='f32'):
             raise ValueError("pack_csr(wire='i16'): the data holds values that are not int16 codes")
         t_sig = fill(False)
     batch = CsrBatch(t_off, t_sig, t_lab, int(all_counts.max()) if all_counts.size else 0)
+    if want_runs and E > 0:
+        batch = batch.with_label_runs(threads) or batch
     return (batch,
             np.concatenate(ptx) if ptx else np.zeros(0, np.int32),
             np.concatenate(pidx) if pidx else np.zeros(0, np.int32))
@@ -359,6 +402,13 @@ class Engine:
         b.pos_offsets = batch.pos_offsets.data_ptr()
         b.signal = batch.signal.data_ptr()
         b.label = batch.label.data_ptr()
+        if batch.run_ends is not None:
+            assert batch.run_ends.dtype == torch.uint16 and batch.run_ends.is_contiguous()
+            assert batch.run_ends.is_cuda == on_dev and batch.run_ends.shape == (P, batch.run_labels.size)
+            b.layout = L.NCB_LAYOUT_CSR_I16_RUNS
+            b.label = batch.run_ends.data_ptr()
+            b.run_labels = batch.run_labels.ctypes.data
+            b.n_runs = batch.run_labels.size
         b.n_vars = batch.signal.shape[1]     # 2, or 3 with the motor-dwell column
         b.n_reads = min(int(batch.max_entries), 0x7fffffff)
         r = results.struct()

@@ -42,6 +42,31 @@ def test_int16_entries_give_the_bits_of_float32_entries(engine_factory, where):
         assert same(a[k], b[k]), k
 
 
+@pytest.mark.parametrize('where', ['host', 'device'])
+def test_label_runs_give_the_results_of_label_bytes(engine_factory, where):
+    """NCB_LAYOUT_CSR_I16_RUNS (4 bytes per entry on the link, labels rebuilt on the device from the run ends
+    of every position) against NCB_LAYOUT_CSR_I16: every result column to the bit, ragged positions, empty
+    positions, a sample without reads on a transcript, warp and CTA classes."""
+    eng = engine_factory(tests=('GMM', 'KS', 'MW', 'TT'), min_coverage=30, dwell_is_raw=True, with_logit=True)
+    rng = np.random.default_rng(21)
+    txs = [make_transcript(rng, P, n, uncalled4=True) for P, n in [(120, 40), (90, 100), (40, 230), (12, 600)]]
+    items = [(t.data, t.samples, t.conditions) for t in txs]
+    # a transcript on which sample 2 has no read at all, and one position without any read
+    d, s, c = items[1]
+    items[1] = (d[:, s != 2], s[s != 2], c[s != 2])
+    items[0][0][5] = np.nan
+    i16 = pack_csr(items, pin=True, wire='i16')[0]
+    runs = pack_csr(items, pin=True, wire='i16r')[0]
+    assert runs.wire == 'i16r' and runs.run_labels.size == 4 and runs.nbytes() < 0.82 * i16.nbytes()
+    if where == 'device':
+        i16, runs = i16.to('cuda'), runs.to('cuda')
+    a = eng.compare_csr(i16, diagnostics=True).numpy()
+    b = eng.compare_csr(runs, diagnostics=True).numpy()
+    assert ((a['status'] & L.NCB_POS_DROP_MASK) == 0).sum() > 200
+    for k in a:
+        assert same(a[k], b[k]), k
+
+
 def test_int16_entries_with_the_motor_dwell_column(engine_factory):
     eng = engine_factory(tests=('GMM', 'KS'), min_coverage=30, dwell_is_raw=True)
     rng = np.random.default_rng(12)

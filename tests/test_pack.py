@@ -96,3 +96,43 @@ def test_int16_wire_refuses_values_that_are_not_codes(bad):
     auto, _, _ = pack_csr(item, wire='auto')           # falls back to float32 entries
     f32, _, _ = pack_csr(item)
     assert auto.wire == 'f32' and np.array_equal(auto.signal.numpy(), f32.signal.numpy(), equal_nan=True)
+
+
+def test_label_runs_of_a_packed_batch():
+    """ncb_pack_label_runs: run ends per position from the label bytes (NCB_LAYOUT_CSR_I16_RUNS); labels that
+    do not come as runs in one common order are refused (such a batch keeps its label bytes)."""
+    import torch
+    from nanocompore_b200 import _lib as L
+    from nanocompore_b200.engine import CsrBatch
+    rng = np.random.default_rng(4)
+    txs = [make_transcript(rng, P, n, uncalled4=True) for P, n in [(60, 30), (25, 200), (7, 3)]]
+    items = [(t.data, t.samples, t.conditions) for t in txs]
+    d, s, c = items[1]
+    items[1] = (d[:, s != 1], s[s != 1], c[s != 1])       # a sample without reads on one transcript
+    items[0][0][3] = np.nan                               # a position without reads
+    plain = pack_csr(items, wire='i16')[0]
+    runs = pack_csr(items, wire='i16r')[0]
+    assert runs.wire == 'i16r' and plain.wire == 'i16'
+    off, lab = plain.pos_offsets.numpy(), plain.label.numpy()
+    ends = runs.run_ends.numpy().astype(np.int64)
+    assert ends.shape == (plain.n_positions, runs.run_labels.size)
+    assert runs.nbytes() == plain.nbytes() - lab.size + 2 * ends.size
+    for p in range(plain.n_positions):
+        seg = lab[off[p]:off[p + 1]]
+        rebuilt = np.repeat(runs.run_labels, np.diff(np.concatenate([[0], ends[p]])))
+        np.testing.assert_array_equal(rebuilt, seg)
+    # out of order inside a position / unknown label / too many runs
+    bad = CsrBatch(plain.pos_offsets, plain.signal, plain.label.clone(), plain.max_entries)
+    n0 = int(off[1])
+    bad.label[:n0] = torch.flip(bad.label[:n0], [0])
+    assert bad.with_label_runs() is None
+    lib = L.load()
+    ends16 = np.zeros((plain.n_positions, 2), np.uint16)
+    two = np.array([lab[0], lab[0] ^ 1], np.uint8)
+    assert lib.ncb_pack_label_runs(off.ctypes.data, lab.ctypes.data, plain.n_positions, two.ctypes.data, 2,
+                                   ends16.ctypes.data, 2) == L.NCB_ERR_INVALID
+    assert lib.ncb_pack_label_runs(off.ctypes.data, lab.ctypes.data, plain.n_positions, two.ctypes.data, 17,
+                                   ends16.ctypes.data, 2) == L.NCB_ERR_INVALID
+    dup = np.array([lab[0], lab[0]], np.uint8)
+    assert lib.ncb_pack_label_runs(off.ctypes.data, lab.ctypes.data, plain.n_positions, dup.ctypes.data, 2,
+                                   ends16.ctypes.data, 2) == L.NCB_ERR_INVALID
