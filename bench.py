@@ -9,7 +9,8 @@ Workload = BASELINE.json configs[2] ("config 3"): synthetic transcripts of 2,000
 replicates x 100 reads per condition, comparison_methods [GMM, KS], the coverage filter (min_coverage 30)
 and log10(dwell) inside the timed path.  The values are what the Uncalled4 reader hands over (int16 tag
 values in a float32 tensor, uncalled4.py:118-192; synthetic.make_transcript(uncalled4=True)), so the
-batches travel as NCB_LAYOUT_CSR_I16 (5 bytes per entry).  One step = ``--batches-per-step`` batches of
+batches travel as NCB_LAYOUT_CSR_I16_RUNS (int16 entries + the label runs of every position: 4 bytes per
+entry; the same entries with a label byte each and as float32 are timed beside it).  One step = ``--batches-per-step`` batches of
 ``--tx-per-batch`` transcripts (default 32 x 50 -> 3.2 M positions: the timed region of K = 20 steps lasts
 ~2 s), taken round-robin from a pool of distinct pinned batches (a batch is ~84 MB, the pool ~1 GB: every
 launch reads data that is not in the 126 MB L2).
@@ -22,8 +23,8 @@ Printed JSON (one line, rank 0):
             H2D copy of the reads, the kernels and the D2H copy of the result columns (``--slots``
             engines on as many streams, so the copies of one batch overlap the kernels of the others),
             the p-value columns kept for the correction, then -- still inside the timed region -- the
-            Benjamini-Hochberg correction over the rows of ALL ranks (sharding.fdr_columns: columns to
-            their owner ranks, GPU sort-scan, q-values back), the q-values copied to the host, and the
+            Benjamini-Hochberg correction over the rows of ALL ranks (sharding.fdr_columns: a sample sort,
+            every rank corrects one value range of every column, q-values back), the q-values copied to the host, and the
             gather of keys + q-values on rank 0 sorted by key (sharding.gather_columns).  Wall clock,
             max over ranks, the job timed three times and the MEDIAN pass reported.  The transcripts of
             the job form ONE global list, sharded over the ranks by sharding.lpt_partition.

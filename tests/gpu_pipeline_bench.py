@@ -45,6 +45,7 @@ def main():
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--repeat', type=int, default=16, help='device path: the task list is the transcripts this many times')
     ap.add_argument('--device-batches', type=int, nargs='+', default=[32, 64, 128])
+    ap.add_argument('--device-only', action='store_true', help='only the device-side decoding pipeline (profiling runs)')
     args = ap.parse_args()
     rng = np.random.default_rng(5)
     with tempfile.TemporaryDirectory() as tmp:
@@ -52,12 +53,18 @@ def main():
         seq = ''.join(rng.choice(list('ACGT'), args.positions))
         transcripts = [Transcript(i + 1, name, seq) for i, (name, _) in enumerate(refs)]
         for kind, paths in (('uncalled4_bam', bams), ('sqlite_db', dbs)):
+            if args.device_only and kind != 'uncalled4_bam':
+                continue
             key = 'bam' if kind == 'uncalled4_bam' else 'db'
             cfg = PathConfig(dict(data={'kd': {'kd1': {key: paths['kd1']}, 'kd2': {key: paths['kd2']}},
                                         'wt': {'wt1': {key: paths['wt1']}, 'wt2': {key: paths['wt2']}}},
                                   depleted_condition='kd', kit='RNA002', comparison_methods=['GMM', 'KS'],
                                   min_coverage=30))
             reader = R.Uncalled4Reader(cfg) if kind == 'uncalled4_bam' else R.DbReader(cfg)
+            if args.device_only:
+                device_pipeline(cfg, reader, transcripts, args)
+                reader.close()
+                continue
             pipe = R.TranscriptPipeline(cfg, reader, TranscriptComparator(cfg, Worker()), 'cuda:0')
             list(pipe.run_stream(transcripts[:2], batch_size=2))          # warm-up: context, buffers
             t0 = time.perf_counter()
