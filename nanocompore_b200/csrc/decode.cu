@@ -21,6 +21,7 @@
 // The per-unit logic is host/device code (decode_core.cuh) that the CPU tests run against the host path.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cub/device/device_scan.cuh>
@@ -62,17 +63,42 @@ struct CudaWarp {
     }
 };
 
-constexpr int INFLATE_WPC = 4;     // warps per CTA of the inflate kernel (4.4 KB of tables each)
+// A group of G lanes as the "warp" of inflate_member (inflate_core.cuh): 32 / G members per warp, each group on its
+// own member, tables and command queue.  The walk of a member's bit stream is one lane's work (91 % of the warp
+// instructions the kernel issues have one active lane), so narrower groups looked like a way to share the walk's
+// instructions among several members -- measured, they are slower: 0.371 / 0.418 / 0.503 / 0.687 ms per transcript
+// at G = 32 / 16 / 8 / 4 (the leaders of a warp do not stay converged through the data-dependent branches of the
+// walk, and the cooperative phases get 32 / G times as many trips).  G = 32 is the default; NCB_INFLATE_GROUP
+// selects the others for A/B runs.
+template <int G>
+struct CudaGroup {
+    unsigned mask;
+    __device__ __forceinline__ CudaGroup() {
+        const int l = threadIdx.x & 31;
+        mask = G == 32 ? FULL : ((G == 32 ? 0u : (1u << (G & 31)) - 1u) << (l & ~(G - 1)));
+    }
+    __device__ __forceinline__ int lane() const { return threadIdx.x & (G - 1); }
+    __device__ __forceinline__ int stride() const { return G; }
+    __device__ __forceinline__ bool leader() const { return (threadIdx.x & (G - 1)) == 0; }
+    __device__ __forceinline__ int bcast(int v) const { return __shfl_sync(mask, v, 0, G); }
+    __device__ __forceinline__ bool any(int v) const { return __any_sync(mask, v) != 0; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ uint8_t load_out(const uint8_t *p) const { return *reinterpret_cast<const volatile uint8_t *>(p); }
+};
+
+constexpr int INFLATE_MEMBERS_PER_CTA = 8;   // 8 x 4.4 KB of tables per CTA, whatever the group width
 constexpr int READ_WPC = 8;
 
-__global__ void __launch_bounds__(INFLATE_WPC * 32)
+template <int G>
+__global__ void __launch_bounds__(INFLATE_MEMBERS_PER_CTA * G)
 inflate_kernel(const BlockDesc *blocks, int n_blocks, const uint32_t *words, uint8_t *text, int32_t *flags) {
-    __shared__ ncb_inflate::Tables tables[INFLATE_WPC];
-    const int b = blockIdx.x * INFLATE_WPC + (threadIdx.x >> 5);
+    __shared__ ncb_inflate::Tables tables[INFLATE_MEMBERS_PER_CTA];
+    const int slot = threadIdx.x / G;
+    const int b = blockIdx.x * INFLATE_MEMBERS_PER_CTA + slot;
     if (b >= n_blocks) return;
     const BlockDesc d = blocks[b];
-    CudaWarp w;
-    const int rc = ncb_inflate::inflate_member(w, tables[threadIdx.x >> 5], words + d.word_off, d.n_words,
+    CudaGroup<G> w;
+    const int rc = ncb_inflate::inflate_member(w, tables[slot], words + d.word_off, d.n_words,
                                                (int64_t)d.cbytes, text + d.dst_off, (int64_t)d.usize);
     if (rc != ncb_inflate::INF_OK && w.leader()) atomicOr(&flags[d.tx], TX_ERROR);
 }
@@ -176,6 +202,7 @@ struct Slot {
 
 struct ncb_decoder {
     int device = 0;
+    int inflate_group = 32;    // lanes per BGZF member in inflate_kernel (NCB_INFLATE_GROUP = 4 / 8 / 16 / 32: A/B runs)
     std::string err;
     std::vector<Slot> slots;
 };
@@ -260,6 +287,10 @@ int ncb_decoder_create(ncb_decoder **out, int device, int n_slots) {
     ncb_decoder *d = new (std::nothrow) ncb_decoder();
     if (!d) return NCB_ERR_NOMEM;
     d->device = device;
+    if (const char *g = getenv("NCB_INFLATE_GROUP")) {
+        const int v = atoi(g);
+        if (v == 4 || v == 8 || v == 16 || v == 32) d->inflate_group = v;
+    }
     try {
         d->slots.resize((size_t)n_slots);
     } catch (const std::exception &) {
@@ -408,8 +439,14 @@ int ncb_decoder_launch(ncb_decoder *d, int slot, int32_t kit_len, int32_t kit_ce
     DCK(cudaMemsetAsync(s.d_recs.ptr, 0, ((size_t)p.n_slots + 1) * sizeof(ReadRec), st));
     s.launches = 0;
     if (nblocks) {
-        inflate_kernel<<<(unsigned)((nblocks + INFLATE_WPC - 1) / INFLATE_WPC), INFLATE_WPC * 32, 0, st>>>(
-            blocks, (int)nblocks, (const uint32_t *)s.d_words.ptr, text, flags);
+        const unsigned grid = (unsigned)((nblocks + INFLATE_MEMBERS_PER_CTA - 1) / INFLATE_MEMBERS_PER_CTA);
+        const uint32_t *words = (const uint32_t *)s.d_words.ptr;
+        switch (d->inflate_group) {
+            case 16: inflate_kernel<16><<<grid, INFLATE_MEMBERS_PER_CTA * 16, 0, st>>>(blocks, (int)nblocks, words, text, flags); break;
+            case 4: inflate_kernel<4><<<grid, INFLATE_MEMBERS_PER_CTA * 4, 0, st>>>(blocks, (int)nblocks, words, text, flags); break;
+            case 8: inflate_kernel<8><<<grid, INFLATE_MEMBERS_PER_CTA * 8, 0, st>>>(blocks, (int)nblocks, words, text, flags); break;
+            default: inflate_kernel<32><<<grid, INFLATE_MEMBERS_PER_CTA * 32, 0, st>>>(blocks, (int)nblocks, words, text, flags); break;
+        }
         ++s.launches;
     }
     if (nspans) {

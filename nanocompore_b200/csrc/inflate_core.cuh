@@ -53,20 +53,23 @@ struct Tables {
 struct BitReader {
     const uint32_t *words;   // 4-byte aligned; words past n_words read as 0
     uint32_t n_words;
-    uint32_t next;           // next word to load
+    uint32_t next;           // next word to enter the buffer
+    uint32_t ahead;          // words[next], loaded when the word before it entered the buffer: the load has a
+                             // refill interval (~4 symbols) to arrive instead of sitting on the walk's chain
     uint64_t buf;
     int cnt;
     int64_t limit_bits;      // bits of the compressed payload
 
     NCB_HD void init(const uint32_t *w, uint32_t nw, int64_t bytes) {
         words = w; n_words = nw; next = 0; buf = 0; cnt = 0; limit_bits = bytes * 8;
+        ahead = nw ? w[0] : 0u;
     }
     NCB_HD void need(int n) {        // n <= 32
         if (cnt < n) {
-            const uint32_t w = next < n_words ? words[next] : 0u;
-            ++next;
-            buf |= (uint64_t)w << cnt;
+            buf |= (uint64_t)ahead << cnt;
             cnt += 32;
+            ++next;
+            ahead = next < n_words ? words[next] : 0u;
         }
     }
     NCB_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
@@ -81,6 +84,7 @@ struct BitReader {
     NCB_HD void align_to_byte() { drop(cnt & 7); }
     NCB_HD void seek_byte(int64_t byte) {      // continue at a byte position of the payload
         next = (uint32_t)(byte >> 2);
+        ahead = next < n_words ? words[next] : 0u;
         buf = 0;
         cnt = 0;
         const int rest = (int)(byte & 3) * 8;
@@ -258,13 +262,6 @@ NCB_HD int build_block_codes(Tables &t) {
 // written to the member's output, `usize` its ISIZE.  Returns the number of commands; *end_of_block is
 // set when the end-of-block code was read, *err on an error.
 NCB_HD int decode_commands(BitReader &br, Tables &t, int64_t produced, int64_t usize, bool *end_of_block, int *err) {
-    const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83,
-                                   99, 115, 131, 163, 195, 227, 258};
-    const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025,
-                                    1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-    const uint8_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12,
-                                    12, 13, 13};
     int n = 0;
     const int64_t start = produced;
     *end_of_block = false;
@@ -284,11 +281,18 @@ NCB_HD int decode_commands(BitReader &br, Tables &t, int64_t produced, int64_t u
             break;
         } else {
             if (sym > 285) { *err = INF_ERR_CODE; break; }
+            // base values and extra bits of RFC 1951 3.2.5 in closed form (tables in local memory would be
+            // initialised at every call): lengths 3..10 and 258 have no extra bits, from code 265 on four codes
+            // share an extra-bit count; distances 1..4 have none, then two codes share one
             const int li = sym - 257;
-            const int len = len_base[li] + (int)br.take(len_extra[li]);
+            const int le = (li < 8 || li == 28) ? 0 : (li >> 2) - 1;
+            const int lb = li == 28 ? 258 : (li < 8 ? li + 3 : 3 + ((4 + (li & 3)) << le));
+            const int len = lb + (int)br.take(le);
             const int ds = decode_dist(br, t);
             if (ds < 0 || ds > 29) { *err = INF_ERR_CODE; break; }
-            const int dist = dist_base[ds] + (int)br.take(dist_extra[ds]);
+            const int de = ds < 4 ? 0 : (ds >> 1) - 1;
+            const int db = ds < 4 ? ds + 1 : 1 + ((2 + (ds & 1)) << de);
+            const int dist = db + (int)br.take(de);
             if ((int64_t)dist > produced) { *err = INF_ERR_DIST; break; }
             if (produced + len > usize) { *err = INF_ERR_OUTPUT; break; }
             t.cmd_len[n] = (uint16_t)len;
@@ -304,6 +308,51 @@ NCB_HD int decode_commands(BitReader &br, Tables &t, int64_t produced, int64_t u
     return n;
 }
 
+
+// decode_commands for a stretch of the stream where nothing unusual happens, with what the walk of one lane
+// spends most of its instructions on taken out of the loop: the end of the payload is checked once per
+// batch of commands instead of once per symbol (behind the payload the reader delivers zeros, and nothing is
+// written to the output before the batch is accepted), offsets and bounds are 32-bit.  Returns the number of
+// commands, or -1 when anything is off (invalid code, distance, output bound, payload overrun): the caller
+// puts the reader back to the start of the batch and lets decode_commands find out what, so errors are
+// reported exactly as before.
+NCB_HD int decode_commands_fast(BitReader &br, Tables &t, int64_t produced, int64_t usize, bool *end_of_block) {
+    const int64_t room64 = usize - produced;
+    const int room = room64 > 0x7fff0000 ? 0x7fff0000 : (int)room64;      // bytes the output still takes
+    const int have = produced > 0x10000 ? 0x10000 : (int)produced;        // bytes a distance may reach back, capped
+    int n = 0, off = 0;
+    *end_of_block = false;
+    t.cmd_off[0] = 0;
+    while (n < MAX_CMDS) {
+        const int sym = decode_lit(br, t);
+        if (sym < 256) {
+            if (sym < 0 || off >= room) return -1;
+            t.cmd_len[n] = 1;
+            t.cmd_val[n] = (uint16_t)sym;
+            t.cmd_off[++n] = (uint16_t)++off;
+        } else if (sym == 256) {
+            *end_of_block = true;
+            break;
+        } else {
+            if (sym > 285) return -1;
+            const int li = sym - 257;
+            const int le = (li < 8 || li == 28) ? 0 : (li >> 2) - 1;
+            const int lb = li == 28 ? 258 : (li < 8 ? li + 3 : 3 + ((4 + (li & 3)) << le));
+            const int len = lb + (int)br.take(le);
+            const int ds = decode_dist(br, t);
+            if (ds < 0 || ds > 29) return -1;
+            const int de = ds < 4 ? 0 : (ds >> 1) - 1;
+            const int db = ds < 4 ? ds + 1 : 1 + ((2 + (ds & 1)) << de);
+            const int dist = db + (int)br.take(de);
+            if (dist > have + off || off + len > room) return -1;
+            t.cmd_len[n] = (uint16_t)len;
+            t.cmd_val[n] = (uint16_t)(dist - 1);
+            off += len;
+            t.cmd_off[++n] = (uint16_t)off;
+        }
+    }
+    return br.overrun() ? -1 : n;
+}
 
 // ---- one member, by a "warp" W ------------------------------------------------------------------
 // W provides lane() / stride() (the lanes share strided loops), leader() (the lane that walks the bit
@@ -370,7 +419,12 @@ NCB_HD int inflate_member(W &w, Tables &t, const uint32_t *words, uint32_t n_wor
             int n = 0;
             if (w.leader()) {
                 bool e = false;
-                n = decode_commands(br, t, produced, usize, &e, &err);
+                const BitReader at_start = br;
+                n = decode_commands_fast(br, t, produced, usize, &e);
+                if (n < 0) {
+                    br = at_start;
+                    n = decode_commands(br, t, produced, usize, &e, &err);
+                }
                 eob = e ? 1 : 0;
             }
             n = w.bcast(n);
