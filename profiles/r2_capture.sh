@@ -20,11 +20,15 @@ echo "reference arm rc=$?"
 
 # parity sweeps (CUDA path vs oracle, every check of tests/test_gpu_parity.py)
 : > $out/${tag}_parity_sweep.jsonl
-timeout 600 python tests/gpu_parity_sweep.py 350 300 16 >> $out/${tag}_parity_sweep.jsonl 2>> $out/${tag}_sweep.err
-timeout 600 python tests/gpu_parity_sweep.py 112 24 16 large >> $out/${tag}_parity_sweep.jsonl 2>> $out/${tag}_sweep.err
-timeout 600 python tests/gpu_parity_sweep.py 400 48 16 csr >> $out/${tag}_parity_sweep.jsonl 2>> $out/${tag}_sweep.err
+timeout 600 python tests/gpu_parity_sweep.py 240 300 16 >> $out/${tag}_parity_sweep.jsonl 2>> $out/${tag}_sweep.err
+timeout 600 python tests/gpu_parity_sweep.py 64 24 16 large >> $out/${tag}_parity_sweep.jsonl 2>> $out/${tag}_sweep.err
+timeout 600 python tests/gpu_parity_sweep.py 240 48 16 csr >> $out/${tag}_parity_sweep.jsonl 2>> $out/${tag}_sweep.err
 timeout 600 python tests/gpu_parity_sweep.py 120 90 16 motor >> $out/${tag}_parity_sweep.jsonl 2>> $out/${tag}_sweep.err
 echo "sweeps done"
+
+# files -> frames (host decoding, device-side decoding)
+timeout 400 python tests/gpu_pipeline_bench.py > $out/${tag}_pipeline.jsonl 2> $out/${tag}_pipeline.err
+echo "pipeline rc=$?"
 
 # launch list + full captures of the top kernels
 if timeout 600 $NCU_BENCH > $out/${tag}_ncu_plain.json 2> $out/${tag}_ncu_plain.err; then
