@@ -27,7 +27,9 @@ Printed JSON (one line, rank 0):
             every rank corrects one value range of every column, q-values back), the q-values copied to the host, and the
             gather of keys + q-values on rank 0 sorted by key (sharding.gather_columns).  Wall clock,
             max over ranks, the job timed three times and the MEDIAN pass reported.  The transcripts of
-            the job form ONE global list, sharded over the ranks by sharding.lpt_partition.
+            the job form ONE global list; with several ranks its batches are handed out by a queue the
+            ranks share (sharding.TaskQueue, list scheduling: a rank the host serves faster runs more of
+            them; ``schedule`` on the line) -- ``--schedule static`` runs sharding.lpt_partition's shards.
   roofline  HBM roofline of the kernel group of a batch that takes longest (live CUDA-event timing of the
             statistics kernels and of each of the three mixture kernels; `kernels` lists all of them,
             `mixture_fit` the three mixture kernels as one), `traffic` from the committed ncu capture; the
@@ -345,6 +347,40 @@ class Rig:
         return tested
 
 
+def _end_to_end_queue(self, host_batches, claim, res_host, consume):
+    """``end_to_end`` over batches handed out by ``claim() -> global batch index | None`` (a queue shared by
+    the ranks): batch g is the pool batch g mod len(host_batches); ``consume(slot, i, g)`` runs when the results
+    of the i-th batch THIS rank took (global index g) are on the host.  Returns (tested positions, [g, ...])."""
+    from nanocompore_b200 import _lib as L
+    tested, taken = 0, []
+    pending = [None] * self.n_slots
+
+    def finish(s):
+        nonlocal tested
+        self.engines[s].wait(self.streams[s])
+        tested += int(np.count_nonzero((res_host[s].status.numpy() & L.NCB_POS_DROP_MASK) == 0))
+        consume(s, *pending[s])
+        pending[s] = None
+
+    while True:
+        s = len(taken) % self.n_slots
+        if pending[s] is not None:
+            finish(s)
+        g = claim()
+        if g is None:
+            break
+        self.engines[s].compare_csr(host_batches[g % len(host_batches)], res_host[s], stream=self.streams[s], wait=False)
+        pending[s] = (len(taken), g)
+        taken.append(g)
+    for s in range(self.n_slots):
+        if pending[s] is not None:
+            finish(s)
+    return tested, taken
+
+
+Rig.end_to_end_queue = _end_to_end_queue
+
+
 def spot_check(tx, res, first_row, methods, min_coverage, n_check=12):
     """Oracle (oracle/comparator.py) on ``n_check`` positions of transcript ``tx``, whose result rows
     start at ``first_row`` of the batch results ``res`` (numpy dict).  Returns (values compared,
@@ -540,29 +576,77 @@ def run_gpu_arm(args):
     res_host = [Results(P, 4, None) for _ in range(NSLOT)]
     pv_rows = [L.PV['KS_INTENSITY'], L.PV['KS_DWELL'], L.PV['GMM_CHI2']]
     n_rows_job = K * B * P
-    job_p = torch.empty((len(pv_rows), n_rows_job), dtype=torch.float64, device=dev)
-    job_q_host = torch.empty((len(pv_rows), n_rows_job), dtype=torch.float64, pin_memory=True)
+    # With several ranks the batches of the job are handed out by a queue shared by the ranks of the box
+    # (sharding.TaskQueue: list scheduling over the global batch list, the reference's task queue of
+    # run.py:104-131): the host does not serve the GPUs of a box evenly (section 6 of DESIGN.md), and a rank
+    # whose copies are faster takes more batches.  A rank holds room for 1.5x its even share.
+    n_batches_global = world * K * B
+    queue = None
+    if world > 1 and args.schedule == 'queue':
+        name = f"/ncb_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+        ok = 1.0
+        try:
+            if rank == 0:
+                queue = sharding.TaskQueue(name, n_batches_global, create=True)
+            barrier()
+            if rank != 0:
+                queue = sharding.TaskQueue(name, n_batches_global)
+        except Exception as e:                       # no shared memory to be had: the static partition
+            print(f"[bench] rank {rank}: task queue unavailable ({e}); static LPT shards", file=sys.stderr)
+            ok = 0.0
+        if over_ranks(ok, dist.ReduceOp.MIN) < 1.0:
+            queue = None
+    cap_batches = K * B if queue is None else min(n_batches_global, (3 * K * B) // 2 + NSLOT)
+    job_p = torch.empty((len(pv_rows), cap_batches * P), dtype=torch.float64, device=dev)
+    job_q_host = torch.empty((len(pv_rows), cap_batches * P), dtype=torch.float64, pin_memory=True)
     # global row key: transcript index in the global list << 32 | position
+    pos_in_tx = torch.arange(N_POSITIONS, device=dev, dtype=torch.int64)
+    keys = torch.empty(cap_batches * P, dtype=torch.int64, device=dev)
     tx_of_row = torch.from_numpy(np.repeat(my_tx, N_POSITIONS)).to(dev)
-    keys = (tx_of_row << 32) | torch.arange(N_POSITIONS, device=dev, dtype=torch.int64).repeat(my_tx.size)
+    keys[:n_rows_job] = (tx_of_row << 32) | pos_in_tx.repeat(my_tx.size)          # the static shard
     del tx_of_row
+    # keys of the batch whose first transcript is number 0 (queue: batch g holds transcripts g T .. g T + T - 1)
+    base_key = (torch.arange(T, device=dev, dtype=torch.int64).repeat_interleave(N_POSITIONS) << 32) | pos_in_tx.repeat(T)
 
-    def job_pass(order, n_rows):
-        """Compare + correction + gather over the batches ``order``; returns (wall ms, tested,
-        stage ms)."""
-        def consume(slot, i):
+    def job_pass(order, n_rows, use_queue=False):
+        """Compare + correction + gather.  The batches are the pool indices ``order`` (this rank's static
+        shard), or, with ``use_queue``, whatever this rank takes from the queue shared by the ranks.
+        Returns (wall ms, tested, stage ms, gather info, batches this rank ran)."""
+        def consume(slot, i, g=None):
             # the p-value columns of the batch join the job's columns on the device (the correction
             # runs there); in-stream, so the next copy-out of the slot cannot overtake it
             with torch.cuda.stream(rig.streams[slot]):
                 for j, r in enumerate(pv_rows):
                     job_p[j, i * P:(i + 1) * P].copy_(res_host[slot].pvalues[r], non_blocking=True)
+                if g is not None:
+                    torch.add(base_key, (g * T) << 32, out=keys[i * P:(i + 1) * P])
+
+        def claim():
+            nonlocal n_taken
+            if n_taken >= cap_batches:
+                return None
+            g = queue.claim()
+            n_taken += g is not None
+            return g
+
+        n_taken = 0
         barrier()
+        if use_queue:
+            if rank == 0:
+                queue.reset()
+            barrier()
         t0 = time.perf_counter()
-        tested = rig.end_to_end(host_pool, order, res_host, consume)
+        if use_queue:
+            tested, taken = rig.end_to_end_queue(host_pool, claim, res_host, consume)
+            n_rows = len(taken) * P
+        else:
+            tested = rig.end_to_end(host_pool, order, res_host, consume)
+            taken = order
         torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
         q = sharding.fdr_columns(job_p[:, :n_rows], bh)
-        job_q_host[:, :n_rows].copy_(q, non_blocking=True)
+        for j in range(len(pv_rows)):      # row by row: a strided block would travel through pageable memory
+            job_q_host[j, :n_rows].copy_(q[j], non_blocking=True)
         torch.cuda.synchronize(dev)
         t2 = time.perf_counter()
         gathered = None
@@ -577,7 +661,16 @@ def run_gpu_arm(args):
         del gathered, q
         return ((t3 - t0) * 1000.0, tested,
                 {"compare_ms": (t1 - t0) * 1000.0, "fdr_ms": (t2 - t1) * 1000.0,
-                 "gather_ms": (t3 - t2) * 1000.0}, info)
+                 "gather_ms": (t3 - t2) * 1000.0}, info, len(taken))
+
+    def per_rank(x):
+        """``x`` of every rank, as a list."""
+        if world == 1:
+            return [float(x)]
+        mine = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        out = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, mine)
+        return [float(v) for v in out.tolist()]
 
     def critical_path(stages):
         """The stage times of the rank that finishes its compare stage LAST, plus the spread of that stage
@@ -604,12 +697,22 @@ def run_gpu_arm(args):
     job_pass(order_w, len(order_w) * P)                 # warm-up: W steps + correction + gather
     E2E_REPEATS = 3
     passes = []
+    if queue is not None:
+        job_pass(None, 0, use_queue=True)               # and once through the queue
     for _ in range(E2E_REPEATS):
-        ms, tested_host, stages, ginfo = job_pass(order_k, n_rows_job)
-        passes.append((max_over_ranks(ms), tested_host, critical_path(stages), ginfo))
+        ms, tested_host, stages, ginfo, n_ran = job_pass(order_k, n_rows_job, use_queue=queue is not None)
+        passes.append((max_over_ranks(ms), tested_host, critical_path(stages), ginfo,
+                       per_rank(n_ran), per_rank(stages["compare_ms"])))
     gc.enable()
     passes.sort(key=lambda x: x[0])
-    ms_e2e, tested_host, stages, ginfo = passes[len(passes) // 2]
+    ms_e2e, tested_host, stages, ginfo, batches_per_rank, compare_ms_per_rank = passes[len(passes) // 2]
+    schedule = {"kind": "queue shared by the ranks (sharding.TaskQueue: list scheduling over the global batch list)"
+                        if queue is not None else "static LPT shards",
+                "batches_per_rank": [int(b) for b in batches_per_rank],
+                "compare_ms_per_rank": compare_ms_per_rank}
+    if queue is not None:
+        barrier()
+        queue.close()
     clocks = sampler.stop()
     total_tested_host = sum_over_ranks(float(tested_host))
     e2e_value = total_tested_host / (ms_e2e / 1000.0)
@@ -619,7 +722,7 @@ def run_gpu_arm(args):
     # (diagnostic, outside the timed passes)
     fdr_stages = {}
     if world > 1:
-        sharding.fdr_columns(job_p[:, :n_rows_job], bh, timings=fdr_stages)
+        sharding.fdr_columns(job_p[:, :min(n_rows_job, int(batches_per_rank[rank]) * P)], bh, timings=fdr_stages)
         fdr_stages = {k: max_over_ranks(v) for k, v in sorted(fdr_stages.items())}
     del job_p, keys
 
@@ -787,6 +890,7 @@ def run_gpu_arm(args):
         "parity_spot_check": check,
         "gpu_launches": total_launches,
         "lpt": lpt,
+        "schedule": schedule,
         "final_gather": None if ginfo is None else dict(ginfo, ms=stages["gather_ms"],
                                                         share_of_job=stages["gather_ms"] / ms_e2e),
         "fdr": {"ms": stages["fdr_ms"], "share_of_job": stages["fdr_ms"] / ms_e2e,
@@ -1063,6 +1167,8 @@ def main():
     ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--skew-heavy', type=int, default=16,
                     help="high-coverage transcripts of the fixed config-5 job (0 = skip it)")
+    ap.add_argument('--schedule', default='queue', choices=['queue', 'static'],
+                    help="N > 1: batches of the end-to-end job from a queue shared by the ranks, or static LPT shards")
     ap.add_argument('--slots', type=int, default=4,
                     help="engines/streams of the end-to-end pipeline (copy-in, kernels, copy-out overlap)")
     ap.add_argument('--ref-positions', type=int, default=N_POSITIONS,

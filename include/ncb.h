@@ -453,6 +453,19 @@ int ncb_timing_mixture(ncb_handle *h, double *ms_init, double *ms_em, double *ms
  * reported against in bench.py. */
 int ncb_probe_fp64_peak(ncb_handle *h, double *tflops, void *stream);
 
+/* Task counter shared by the worker processes of one box: the reference hands transcripts to its workers
+ * through a multiprocessing queue (run.py:104-131, 380-420), so a worker that is served faster by the host takes
+ * more of them; with one process per GPU the same is a 64-bit counter in POSIX shared memory that every rank
+ * advances with an atomic fetch-add (list scheduling over a task list every rank knows: sharding.TaskQueue).
+ * ncb_counter_open maps the counter `name` ("/..."; `create` != 0: creates it if need be and sets it to 0);
+ * ncb_counter_add returns the value BEFORE the addition; ncb_counter_close unmaps it and, with `unlink` != 0,
+ * removes the name.  Host only. */
+typedef struct ncb_counter ncb_counter;
+int ncb_counter_open(const char *name, int create, ncb_counter **out);
+int64_t ncb_counter_add(ncb_counter *c, int64_t n);
+void ncb_counter_set(ncb_counter *c, int64_t value);
+void ncb_counter_close(ncb_counter *c, int unlink);
+
 #ifdef __cplusplus
 }
 #endif

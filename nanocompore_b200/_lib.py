@@ -60,7 +60,8 @@ EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 
            'ncb_probe_fp64_peak',
            'ncb_decoder_create', 'ncb_decoder_destroy', 'ncb_decoder_last_error', 'ncb_decoder_stage',
            'ncb_decoder_launch', 'ncb_decoder_collect', 'ncb_decoder_staged_bytes', 'ncb_decoder_kernel_launches',
-           'ncb_decoder_download']
+           'ncb_decoder_download',
+           'ncb_counter_open', 'ncb_counter_add', 'ncb_counter_set', 'ncb_counter_close']
 
 
 class NcbOpts(C.Structure):
@@ -149,6 +150,14 @@ def load(path=None):
     lib.ncb_pack_rows_fill_i16.restype = C.c_int
     lib.ncb_pack_label_runs.argtypes = [vp, vp, i64, vp, i32, vp, C.c_int]
     lib.ncb_pack_label_runs.restype = C.c_int
+    lib.ncb_counter_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    lib.ncb_counter_open.restype = C.c_int
+    lib.ncb_counter_add.argtypes = [vp, i64]
+    lib.ncb_counter_add.restype = i64
+    lib.ncb_counter_set.argtypes = [vp, i64]
+    lib.ncb_counter_set.restype = None
+    lib.ncb_counter_close.argtypes = [vp, C.c_int]
+    lib.ncb_counter_close.restype = None
     lib.ncb_results_host_bytes.argtypes = [vp, i64, i32, C.c_int]
     lib.ncb_results_host_bytes.restype = i64
     lib.ncb_pack_rows_count.argtypes = [vp, vp, i64, i64, i32, vp, C.c_int]

@@ -20,7 +20,7 @@ INCLUDE = os.path.join(ROOT, 'include')
 OBJDIR = os.path.join(ROOT, 'build', 'ncb')
 LIB = os.path.join(HERE, 'libncb.so')
 
-SOURCES = ['position_kernel.cu', 'gmm_split.cu', 'ks_pvalue.cu', 'fdr.cu', 'context.cu', 'api.cu', 'pack.cu', 'reader.cu', 'decode.cu']
+SOURCES = ['position_kernel.cu', 'gmm_split.cu', 'ks_pvalue.cu', 'fdr.cu', 'context.cu', 'api.cu', 'pack.cu', 'reader.cu', 'decode.cu', 'taskq.cu']
 HEADERS = [os.path.join(CSRC, h) for h in ('ncb_internal.h', 'ncb_math.cuh', 'group_ops.cuh', 'gmm_common.cuh', 'bam_internal.h',
                                                'inflate_core.cuh', 'decode_core.cuh', 'decode_stage.h')] + \
           [os.path.join(INCLUDE, 'ncb.h')]
@@ -75,7 +75,7 @@ def build(force=False, verbose=False, defines=(), lib=None, objdir=None):
             if verbose and out:
                 print(out)
     if force or jobs or _stale(LIB, objs):
-        run([exe, '-shared', '-o', LIB] + objs + ['-lcudart', '-lpthread', '-lz'])
+        run([exe, '-shared', '-o', LIB] + objs + ['-lcudart', '-lpthread', '-lz', '-lrt'])
     return LIB
 
 

@@ -19,7 +19,11 @@ NCCL / NVLink (gloo in the CPU tests):
   * ``gather_columns``  the result columns of every rank on one rank, rows sorted by a global key
                         (so the table does not depend on the sharding).
 
-Both use pre-sized buffers and collectives only (``all_gather_into_tensor`` /
+``TaskQueue`` is the dynamic alternative to a fixed partition: the task list (heaviest first) is known to
+every rank and a counter in shared memory hands out its next entry, so a rank the host serves faster takes more
+tasks -- what the reference's task queue does for its worker processes (run.py:104-131).
+
+Both exchanges use pre-sized buffers and collectives only (``all_gather_into_tensor`` /
 ``all_to_all_single``): one communicator-wide operation each, no per-peer send/recv lists.
 ``warm_up`` runs them once on a few elements so that NCCL sets its channels up before a timed job.
 """
@@ -56,6 +60,54 @@ def lpt_partition(work, world_size):
         shards[r].append(int(t))
         load[r] += work[t]
     return [np.array(sorted(s), dtype=np.int64) for s in shards]
+
+
+class TaskQueue:
+    """Cursor over a task list shared by the ranks of one box (``ncb_counter_*``: a 64-bit word in POSIX shared
+    memory, atomic fetch-add).  Every rank holds the same list (e.g. ``lpt_order(work)``: heaviest first, so that
+    handing the next task to whichever rank is free is list scheduling); ``claim()`` returns the index of the
+    next task nobody has taken, or None when the list is exhausted.
+
+    ``name``: the same on every rank of the job and different between jobs that run at the same time (bench.py
+    derives it from MASTER_PORT); rank 0 passes ``create=True`` BEFORE the others open it (a barrier in between)
+    and calls ``reset`` between passes over the list (again with barriers on both sides)."""
+
+    def __init__(self, name, n_tasks, create=False):
+        from nanocompore_b200 import _lib as L
+        import ctypes as C
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        self.name = name if name.startswith('/') else '/' + name
+        self.n_tasks = int(n_tasks)
+        self._owner = bool(create)
+        rc = self._lib.ncb_counter_open(self.name.encode(), int(create), C.byref(self._h))
+        if rc != L.NCB_OK:
+            raise L.NcbError(rc, f"ncb_counter_open({self.name!r})")
+
+    def claim(self, n=1):
+        """First index of the next ``n`` tasks (the caller gets [i, min(i + n, n_tasks))), or None."""
+        i = int(self._lib.ncb_counter_add(self._h, int(n)))
+        return i if i < self.n_tasks else None
+
+    def reset(self, value=0):
+        self._lib.ncb_counter_set(self._h, int(value))
+
+    def close(self):
+        if self._h:
+            self._lib.ncb_counter_close(self._h, int(self._owner))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def lpt_order(work):
+    """Task indices, heaviest first (ties by index): the order a ``TaskQueue`` hands them out in."""
+    work = np.asarray(work, dtype=np.float64)
+    return np.lexsort((np.arange(work.size), -work))
 
 
 def lpt_imbalance(work, shards):

@@ -173,3 +173,49 @@ def test_sample_rows_stays_inside_large_shards():
         assert pick.dtype == torch.int64 and pick.numel() == sharding.FDR_SAMPLE
         assert int(pick[0]) == 0 and int(pick[-1]) == n - 1
         assert bool((pick[1:] >= pick[:-1]).all()) and int(pick.max()) < n
+
+
+def _claim_all(name, n_tasks, out):
+    import time
+    from nanocompore_b200.sharding import TaskQueue
+    q = TaskQueue(name, n_tasks)
+    mine = []
+    while True:
+        i = q.claim()
+        if i is None:
+            break
+        mine.append(i)
+        if len(mine) % 64 == 0:
+            time.sleep(0)
+    q.close()
+    out.put(mine)
+
+
+def test_task_queue_hands_every_task_to_exactly_one_process():
+    """sharding.TaskQueue (ncb_counter_*: fetch-add on a word in POSIX shared memory): four processes claim from
+    one list; every task is taken once, the counter can be reset for another pass, the name disappears with its
+    owner."""
+    import multiprocessing as mp
+    import os
+    from nanocompore_b200.sharding import TaskQueue, lpt_order
+    name = f"/ncb_test_queue_{os.getpid()}"
+    n_tasks = 20000
+    owner = TaskQueue(name, n_tasks, create=True)
+    ctx = mp.get_context('spawn')
+    for _ in range(2):                                   # two passes over the list
+        owner.reset()
+        out = ctx.Queue()
+        procs = [ctx.Process(target=_claim_all, args=(name, n_tasks, out)) for _ in range(4)]
+        for p in procs:
+            p.start()
+        got = [out.get(timeout=120) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        taken = np.sort(np.concatenate([np.asarray(g, dtype=np.int64) for g in got]))
+        assert np.array_equal(taken, np.arange(n_tasks))
+    assert owner.claim() is None
+    owner.close()
+    assert not os.path.exists('/dev/shm' + name)
+    with pytest.raises(Exception):
+        TaskQueue(name, n_tasks)                         # nobody created it
+    assert list(lpt_order([1.0, 5.0, 5.0, 2.0])) == [1, 2, 3, 0]
