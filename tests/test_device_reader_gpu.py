@@ -99,9 +99,12 @@ def test_pipeline_frames_equal_the_host_pipeline(tmp_path):
         for (_, a), (_, b) in zip(got, want):
             frames_equal(a, b)
         assert got[3][1] is None and sum(len(df) for _, df in got[:3]) > 300
-        streamed = list(pipe.run_stream(transcripts, batch_size=2))
-        for (_, a), (_, b) in zip(streamed, want):
-            frames_equal(a, b)
+        # three batches in flight: two batches, then one transcript per batch (the slots wrap around)
+        for batch_size in (2, 1):
+            streamed = list(pipe.run_stream(transcripts, batch_size=batch_size))
+            assert [t.name for t, _ in streamed] == [t.name for t in transcripts]
+            for (_, a), (_, b) in zip(streamed, want):
+                frames_equal(a, b)
         pipe.close()
         reader.close()
 
