@@ -585,16 +585,24 @@ def run_gpu_arm(args):
     if world > 1 and args.schedule == 'queue':
         name = f"/ncb_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
         ok = 1.0
-        try:
-            if rank == 0:
-                queue = sharding.TaskQueue(name, n_batches_global, create=True)
-            barrier()
-            if rank != 0:
-                queue = sharding.TaskQueue(name, n_batches_global)
-        except Exception as e:                       # no shared memory to be had: the static partition
-            print(f"[bench] rank {rank}: task queue unavailable ({e}); static LPT shards", file=sys.stderr)
-            ok = 0.0
+
+        def open_queue(create):
+            nonlocal queue, ok
+            try:
+                queue = sharding.TaskQueue(name, n_batches_global, create=create)
+            except Exception as e:                   # no shared memory to be had: the static partition
+                print(f"[bench] rank {rank}: task queue unavailable ({e}); static LPT shards", file=sys.stderr)
+                ok = 0.0
+
+        # every rank passes the same collectives whatever happens to its own open
+        if rank == 0:
+            open_queue(True)
+        barrier()
+        if rank != 0:
+            open_queue(False)
         if over_ranks(ok, dist.ReduceOp.MIN) < 1.0:
+            if queue is not None:
+                queue.close()
             queue = None
     cap_batches = K * B if queue is None else min(n_batches_global, (3 * K * B) // 2 + NSLOT)
     job_p = torch.empty((len(pv_rows), cap_batches * P), dtype=torch.float64, device=dev)
