@@ -226,6 +226,11 @@ typedef struct {
 /* --- lifecycle ------------------------------------------------------------------ */
 
 int ncb_abi_version(void);
+/* sizeof(ncb_opts), sizeof(ncb_batch), sizeof(ncb_results) as this library was built: a binding checks its own
+ * struct definitions against them (ncb_default_opts writes a whole ncb_opts). */
+int ncb_sizeof_opts(void);
+int ncb_sizeof_batch(void);
+int ncb_sizeof_results(void);
 
 /* Fills *opts with the reference's defaults (config.py:196-214): tests = GMM|KS,
  * n_samples = 4, min_coverage = 30, hard counts, 100 EM iterations, tol 1e-3, reg_covar 1e-6. */

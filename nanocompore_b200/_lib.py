@@ -48,7 +48,7 @@ DF = dict(BIC1=0, BIC2=1, W0=2, MU0_X=3, MU0_Y=4, C0_XX=5, C0_XY=6, C0_YY=7,
           MEAN2_X=13, MEAN2_Y=14, STD2_X=15, STD2_Y=16)
 NCB_DF_ROWS = 17
 
-EXPORTS = ['ncb_abi_version', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
+EXPORTS = ['ncb_abi_version', 'ncb_sizeof_opts', 'ncb_sizeof_batch', 'ncb_sizeof_results', 'ncb_default_opts', 'ncb_create', 'ncb_set_opts', 'ncb_destroy',
            'ncb_last_error', 'ncb_compare', 'ncb_wait', 'ncb_results_host_bytes',
            'ncb_pack_fill_i16', 'ncb_pack_rows_fill_i16', 'ncb_pack_label_runs', 'ncb_ks_exact_pvalues', 'ncb_bh_fdr', 'ncb_bh_fdr_segment',
            'ncb_context_combine',
@@ -206,6 +206,10 @@ def load(path=None):
     lib.ncb_decoder_download.restype = C.c_int
     if lib.ncb_abi_version() != NCB_ABI_VERSION:
         raise RuntimeError("libncb.so ABI version mismatch: rebuild with python -m nanocompore_b200.build")
+    for fn, struct in ((lib.ncb_sizeof_opts, NcbOpts), (lib.ncb_sizeof_batch, NcbBatch), (lib.ncb_sizeof_results, NcbResults)):
+        fn.restype = C.c_int
+        if fn() != C.sizeof(struct):
+            raise RuntimeError(f"{path}: {struct.__name__} is {C.sizeof(struct)} bytes here, {fn()} in the library")
     _libs[path] = lib
     return lib
 

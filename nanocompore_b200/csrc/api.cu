@@ -142,6 +142,9 @@ static void release(DevBuf &b) {
 extern "C" {
 
 int ncb_abi_version(void) { return NCB_ABI_VERSION; }
+int ncb_sizeof_opts(void) { return (int)sizeof(ncb_opts); }
+int ncb_sizeof_batch(void) { return (int)sizeof(ncb_batch); }
+int ncb_sizeof_results(void) { return (int)sizeof(ncb_results); }
 
 void ncb_default_opts(ncb_opts *o) {
     if (!o) return;

@@ -86,3 +86,24 @@ def test_product_never_imports_the_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     text = f.read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), fn
+
+
+def test_struct_sizes_of_the_binding_and_of_the_documented_stub():
+    """The library reports sizeof(ncb_opts / ncb_batch / ncb_results); the package's ctypes structures and the ones
+    of the stub printed in INTEGRATION.md section 2 (executed here up to its first GPU call) have those sizes --
+    ncb_default_opts writes a whole ncb_opts into the caller's struct."""
+    import ctypes as C
+    import re
+    lib = L.load()
+    assert lib.ncb_sizeof_opts() == C.sizeof(L.NcbOpts)
+    assert lib.ncb_sizeof_batch() == C.sizeof(L.NcbBatch)
+    assert lib.ncb_sizeof_results() == C.sizeof(L.NcbResults)
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    code = re.search(r"```python\n# nanocompore/_ncb.py\n(.*?)```", text, flags=re.S).group(1)
+    code = code.replace("C.CDLL('libncb.so')", f"C.CDLL({L.LIB_PATH!r})")
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md', 'exec'), ns)        # class definitions, CDLL, the size assertion
+    assert C.sizeof(ns['Opts']) == lib.ncb_sizeof_opts() and C.sizeof(ns['Batch']) == lib.ncb_sizeof_batch()
+    o = ns['Opts']()
+    ns['lib'].ncb_default_opts(C.byref(o))
+    assert o.struct_size == C.sizeof(ns['Opts']) and o.em_max_iter == 100
