@@ -12,7 +12,7 @@ values in a float32 tensor, uncalled4.py:118-192; synthetic.make_transcript(unca
 batches travel as NCB_LAYOUT_CSR_I16_RUNS (int16 entries + the label runs of every position: 4 bytes per
 entry; the same entries with a label byte each and as float32 are timed beside it).  One step = ``--batches-per-step`` batches of
 ``--tx-per-batch`` transcripts (default 32 x 50 -> 3.2 M positions: the timed region of K = 20 steps lasts
-~1.5 s, the end-to-end job ~1.6 s per pass, three passes), taken round-robin from a pool of distinct pinned batches (a batch is ~84 MB, the pool ~1 GB: every
+~1.5 s, the end-to-end job ~1.6 s per pass, three passes), taken round-robin from a pool of distinct pinned batches (a batch is ~68 MB, the pool ~0.8 GB: every
 launch reads data that is not in the 126 MB L2).
 
 Printed JSON (one line, rank 0):
